@@ -1,0 +1,150 @@
+"""ctypes front-end of ``libo3d_oracle.so`` (TEST INFRASTRUCTURE, see o3d_oracle.c)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libo3d_oracle.so")
+_lib = None
+
+
+def build(force: bool = False) -> str:
+    """Compile the C oracle in place (gcc, -ffp-contract=off)."""
+    if force or not os.path.exists(_LIB_PATH) or (
+        os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(os.path.join(_HERE, f)) for f in ("o3d_oracle.c", "mc_tables.h"))
+    ):
+        subprocess.run(["make", "-C", _HERE, "-B"], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(_LIB_PATH)
+        p = C.c_void_p
+        L.orc_num_threads.restype = C.c_int
+        L.orc_set_num_threads.argtypes = [C.c_int]
+        L.orc_depth_from_u16.argtypes = [p, C.c_size_t, C.c_double, C.c_double, p]
+        L.orc_backproject.restype = C.c_int64
+        L.orc_backproject.argtypes = [p, p, C.c_int, C.c_int, p, p, C.c_int, C.c_int, p, p]
+        L.orc_tsdf_integrate.restype = C.c_int64
+        L.orc_tsdf_integrate.argtypes = [p, p, p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                                         p, p, p, C.c_int, C.c_int, p, p, C.c_int]
+        L.orc_extract_mesh.argtypes = [p, p, p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, p,
+                                       p, p, p, C.c_int64, p, C.c_int64, p]
+        L.orc_extract_points.restype = C.c_int64
+        L.orc_extract_points.argtypes = [p, p, p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, p,
+                                         p, p, p, p, C.c_int64]
+        L.orc_count_occupied.restype = C.c_int64
+        L.orc_count_occupied.argtypes = [p, C.c_size_t]
+        _lib = L
+    return _lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def num_threads() -> int:
+    return lib().orc_num_threads()
+
+
+def set_num_threads(n: int) -> None:
+    lib().orc_set_num_threads(int(n))
+
+
+def depth_from_u16(depth_u16, depth_scale=1000.0, depth_trunc=3.0):
+    """Appendix A.1 -- reference call site N/3DM/slam_utils.py:212-220."""
+    a = np.ascontiguousarray(depth_u16, dtype=np.uint16)
+    out = np.empty(a.shape, np.float32)
+    lib().orc_depth_from_u16(_ptr(a), a.size, float(depth_scale), float(depth_trunc), _ptr(out))
+    return out
+
+
+def backproject(depth_f32, K, extrinsic=None, rgb=None, stride=1, valid_only=True):
+    """Appendix A.2 -- N/3DM/mapping_module.py:37,41 / N/3DM/scaling_system.py:72-77.
+
+    K = (fx, fy, cx, cy); extrinsic = world->camera 4x4 (f64).  Returns (xyz f64 [M,3], rgb f64 [M,3] | None).
+    """
+    d = np.ascontiguousarray(depth_f32, dtype=np.float32)
+    H, W = d.shape
+    Kd = np.ascontiguousarray(K, dtype=np.float64)
+    E = np.eye(4) if extrinsic is None else np.asarray(extrinsic, dtype=np.float64)
+    M = np.ascontiguousarray(np.linalg.inv(E))
+    rows = ((H + stride - 1) // stride) * ((W + stride - 1) // stride)
+    xyz = np.empty((rows, 3), np.float64)
+    c = None
+    col = None
+    if rgb is not None:
+        c = np.ascontiguousarray(rgb, dtype=np.uint8)
+        col = np.empty((rows, 3), np.float64)
+    n = lib().orc_backproject(_ptr(d), _ptr(c), W, H, _ptr(Kd), _ptr(M), int(stride), int(bool(valid_only)), _ptr(xyz), _ptr(col))
+    return xyz[:n], (None if col is None else col[:n])
+
+
+class Volume:
+    """Dense TSDF box in Open3D order idx=(x*ny+y)*nz+z (UniformTSDFVolume semantics, A.3-A.5)."""
+
+    def __init__(self, resolution, voxel_length, sdf_trunc, origin=(0.0, 0.0, 0.0), gz0=0, with_color=False):
+        if np.isscalar(resolution):
+            resolution = (int(resolution),) * 3
+        self.nx, self.ny, self.nz = (int(r) for r in resolution)
+        self.voxel_length = float(voxel_length)
+        self.sdf_trunc = float(sdf_trunc)
+        self.origin = np.ascontiguousarray(origin, dtype=np.float64)
+        self.gz0 = int(gz0)
+        n = self.nx * self.ny * self.nz
+        self.tsdf = np.zeros(n, np.float32)
+        self.weight = np.zeros(n, np.float32)
+        self.color = np.zeros(n * 3, np.float32) if with_color else None
+
+    def integrate(self, depth_f32, K, extrinsic, rgb=None, z_restart=8) -> int:
+        d = np.ascontiguousarray(depth_f32, dtype=np.float32)
+        H, W = d.shape
+        Kd = np.ascontiguousarray(K, dtype=np.float64)
+        E = np.ascontiguousarray(extrinsic, dtype=np.float64)
+        c = None if rgb is None else np.ascontiguousarray(rgb, dtype=np.uint8)
+        return lib().orc_tsdf_integrate(_ptr(self.tsdf), _ptr(self.weight), _ptr(self.color if c is not None else None),
+                                        self.nx, self.ny, self.nz, self.gz0, self.voxel_length, self.sdf_trunc,
+                                        _ptr(self.origin), _ptr(d), _ptr(c), W, H, _ptr(Kd), _ptr(E), int(z_restart))
+
+    def grid(self, name="tsdf"):
+        return getattr(self, name).reshape(self.nx, self.ny, self.nz)
+
+    def occupied(self) -> int:
+        return lib().orc_count_occupied(_ptr(self.weight), self.weight.size)
+
+    def extract_mesh(self):
+        cap_v, cap_t = 1 << 16, 1 << 17
+        while True:
+            v = np.empty((cap_v, 3), np.float64)
+            key = np.empty((cap_v, 4), np.int32)
+            col = np.empty((cap_v, 3), np.float64) if self.color is not None else None
+            t = np.empty((cap_t, 3), np.int32)
+            cnt = np.zeros(2, np.int64)
+            lib().orc_extract_mesh(_ptr(self.tsdf), _ptr(self.weight), _ptr(self.color), self.nx, self.ny, self.nz,
+                                   self.gz0, self.voxel_length, _ptr(self.origin), _ptr(v), _ptr(key), _ptr(col),
+                                   cap_v, _ptr(t), cap_t, _ptr(cnt))
+            nv, nt = int(cnt[0]), int(cnt[1])
+            if nv <= cap_v and nt <= cap_t:
+                return {"vertices": v[:nv], "keys": key[:nv], "triangles": t[:nt],
+                        "colors": None if col is None else col[:nv]}
+            cap_v, cap_t = max(cap_v, nv), max(cap_t, nt)
+
+    def extract_points(self, normals=True):
+        cap = 1 << 16
+        while True:
+            p = np.empty((cap, 3), np.float64)
+            nrm = np.empty((cap, 3), np.float64) if normals else None
+            col = np.empty((cap, 3), np.float64) if self.color is not None else None
+            key = np.empty((cap, 4), np.int32)
+            n = lib().orc_extract_points(_ptr(self.tsdf), _ptr(self.weight), _ptr(self.color), self.nx, self.ny,
+                                         self.nz, self.gz0, self.voxel_length, _ptr(self.origin), _ptr(p), _ptr(nrm),
+                                         _ptr(col), _ptr(key), cap)
+            if n <= cap:
+                return {"points": p[:n], "normals": None if nrm is None else nrm[:n],
+                        "colors": None if col is None else col[:n], "keys": key[:n]}
+            cap = int(n)

@@ -1,0 +1,370 @@
+/*
+ * oracle/o3d_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * CPU restatement of the arithmetic behind BodySLAM's 3DM hot path.  The
+ * reference delegates every one of these steps to Open3D (unpinned in
+ * N/requirements.txt:12, not vendored under /root/reference, not installable
+ * offline), so this file restates Open3D's legacy-pipeline semantics
+ *  and anchors on the reference's own call sites:
+ *
+ *   orc_depth_from_u16   <- RGBDImage.create_from_color_and_depth(depth_scale, depth_trunc)
+ *                           N/3DM/slam_utils.py:212-220            (Appendix A.1)
+ *   orc_backproject      <- PointCloud.create_from_depth_image / pixel_to_3d
+ *                           N/3DM/mapping_module.py:37,41 ; N/3DM/scaling_system.py:72-77 (A.2)
+ *   orc_tsdf_integrate   <- TSDF.build_3D_map -> volume.integrate   N/3DM/tsdf.py:14-22 (A.3)
+ *   orc_extract_mesh     <- TSDF.extract_mesh                       N/3DM/tsdf.py:42-43 (A.4)
+ *   orc_extract_points   <- TSDF.extract_pcd                        N/3DM/tsdf.py:39-40 (A.5)
+ *
+ * PARITY STATUS: *unpinned* against real Open3D for these five functions -- the
+ * reference holds no test, fixture or recorded output for them
+ * and Open3D cannot be imported here.  The oracle therefore DEFINES the order of
+ * floating point operations (no FMA contraction: build with -ffp-contract=off).
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl
+ * reference legs may load this library.
+ *
+ * Volume layout: dense box of nx*ny*nz voxels, Open3D order  idx = (x*ny + y)*nz + z.
+ * The box may be a z-slab of a larger grid: local z maps to global z = gz0 + z.
+ * World position of global voxel (X,Y,Z) centre = origin + (X+0.5, Y+0.5, Z+0.5)*voxel_length.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include "mc_tables.h"
+
+#define ORC_API __attribute__((visibility("default")))
+
+ORC_API int orc_num_threads(void) {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+ORC_API void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
+/* ------------------------------------------------------------------ A.1 */
+/* u16 -> f32 plain cast, divide by (float)depth_scale, zero when >= depth_trunc. */
+ORC_API void orc_depth_from_u16(const uint16_t *in, size_t n, double depth_scale,
+                                double depth_trunc, float *out) {
+    const float scale_f = (float)depth_scale;
+    for (size_t i = 0; i < n; ++i) {
+        float p = (float)in[i];
+        p /= scale_f;
+        if ((double)p >= depth_trunc) p = 0.0f;
+        out[i] = p;
+    }
+}
+
+/* ------------------------------------------------------------------ A.2 */
+/* cam_to_world = inverse(extrinsic) (row-major 4x4, f64), K = {fx, fy, cx, cy}.
+ * Row-major scan, step `stride`; d > 0 pixels are emitted in order.  With
+ * valid_only == 0 every visited pixel produces a row (NaN for d <= 0).
+ * rgb (H*W*3 u8) may be NULL; colours are c/255 as f64.  Returns the number of rows. */
+ORC_API int64_t orc_backproject(const float *depth, const uint8_t *rgb, int W, int H,
+                                const double *K, const double *cam_to_world, int stride,
+                                int valid_only, double *out_xyz, double *out_rgb) {
+    const double fx = K[0], fy = K[1], cx = K[2], cy = K[3];
+    const double *M = cam_to_world;
+    int64_t n = 0;
+    for (int i = 0; i < H; i += stride) {
+        for (int j = 0; j < W; j += stride) {
+            const float p = depth[(size_t)i * W + j];
+            if (p > 0) {
+                const double z = (double)p;
+                const double x = (j - cx) * z / fx;
+                const double y = (i - cy) * z / fy;
+                for (int r = 0; r < 3; ++r)
+                    out_xyz[3 * n + r] = ((M[4 * r + 0] * x + M[4 * r + 1] * y) + M[4 * r + 2] * z) + M[4 * r + 3];
+                if (rgb && out_rgb)
+                    for (int c = 0; c < 3; ++c)
+                        out_rgb[3 * n + c] = rgb[((size_t)i * W + j) * 3 + c] / 255.0;
+                ++n;
+            } else if (!valid_only) {
+                for (int r = 0; r < 3; ++r) out_xyz[3 * n + r] = NAN;
+                if (rgb && out_rgb)
+                    for (int c = 0; c < 3; ++c) out_rgb[3 * n + c] = NAN;
+                ++n;
+            }
+        }
+    }
+    return n;
+}
+
+/* ------------------------------------------------------------------ A.3 */
+/*
+ * One frame into the dense box.  z_restart R: the float32 camera-space point of a
+ * voxel column is evaluated directly (E*p) at every GLOBAL z that is a multiple
+ * of R and advanced by the float32 increment E[:,2]*voxel_length in between;
+ * R <= 0 is Open3D's literal loop (direct evaluation at global z = 0 only).
+ * color: optional nx*ny*nz*3 f32 running mean of rgb (Open3D keeps f64; the
+ * product keeps f32 -- see DESIGN.md), rgb: optional H*W*3 u8.
+ * Returns the number of voxels updated by this frame (U_f of SURVEY.md 8d).
+ */
+ORC_API int64_t orc_tsdf_integrate(float *tsdf, float *weight, float *color, int nx, int ny,
+                                   int nz, int gz0, double voxel_length, double sdf_trunc,
+                                   const double *origin, const float *depth, const uint8_t *rgb,
+                                   int W, int H, const double *K, const double *extrinsic,
+                                   int z_restart) {
+    const float fx = (float)K[0], fy = (float)K[1], cx = (float)K[2], cy = (float)K[3];
+    float E[16];
+    for (int i = 0; i < 16; ++i) E[i] = (float)extrinsic[i];
+    const float vl = (float)voxel_length;
+    const float half = vl * 0.5f;
+    const float trunc_f = (float)sdf_trunc;
+    const float trunc_inv = 1.0f / trunc_f;
+    const float dzx = E[2] * vl, dzy = E[6] * vl, dzz = E[10] * vl; /* E_scaled(:,2) */
+    const float safe_w = W - 0.0001f, safe_h = H - 0.0001f;
+    const float fxi = 1.0f / fx, fyi = 1.0f / fy;
+    int64_t updated = 0;
+
+#pragma omp parallel for schedule(static) reduction(+ : updated)
+    for (int x = 0; x < nx; ++x) {
+        for (int y = 0; y < ny; ++y) {
+            const float px = (float)((double)(half + vl * (float)x) + origin[0]);
+            const float py = (float)((double)(half + vl * (float)y) + origin[1]);
+            float pcx = 0.f, pcy = 0.f, pcz = 0.f;
+            /* literal mode: march from global z = 0 up to the slab base */
+            int need_direct = 1;
+            int gz_begin = gz0;
+            if (z_restart <= 0 && gz0 > 0) gz_begin = 0;
+            for (int gz = gz_begin; gz < gz0 + nz; ++gz) {
+                if (need_direct || (z_restart > 0 && gz % z_restart == 0)) {
+                    const float pz = (float)((double)(half + vl * (float)gz) + origin[2]);
+                    pcx = ((E[0] * px + E[1] * py) + E[2] * pz) + E[3];
+                    pcy = ((E[4] * px + E[5] * py) + E[6] * pz) + E[7];
+                    pcz = ((E[8] * px + E[9] * py) + E[10] * pz) + E[11];
+                    need_direct = 0;
+                }
+                const float cxp = pcx, cyp = pcy, czp = pcz;
+                pcx += dzx; pcy += dzy; pcz += dzz; /* value for gz+1 */
+                if (gz < gz0) continue;
+                if (czp <= 0) continue;
+                const float u_f = cxp * fx / czp + cx + 0.5f;
+                const float v_f = cyp * fy / czp + cy + 0.5f;
+                if (!(u_f >= 0.0001f && u_f < safe_w && v_f >= 0.0001f && v_f < safe_h)) continue;
+                const int u = (int)u_f, v = (int)v_f;
+                const float d = depth[(size_t)v * W + u];
+                if (d <= 0.0f) continue;
+                const float xx = ((float)u - cx) * fxi, yy = ((float)v - cy) * fyi;
+                const float mult = sqrtf((xx * xx + yy * yy) + 1.0f);
+                const float sdf = (d - czp) * mult;
+                if (sdf > -trunc_f) {
+                    const size_t idx = ((size_t)x * ny + y) * nz + (gz - gz0);
+                    const float t = fminf(1.0f, sdf * trunc_inv);
+                    const float w = weight[idx];
+                    if (color && rgb) {
+                        const uint8_t *c = rgb + ((size_t)v * W + u) * 3;
+                        for (int k = 0; k < 3; ++k)
+                            color[3 * idx + k] = (color[3 * idx + k] * w + (float)c[k]) / (w + 1.0f);
+                    }
+                    tsdf[idx] = (tsdf[idx] * w + t) / (w + 1.0f);
+                    weight[idx] = w + 1.0f;
+                    ++updated;
+                }
+            }
+        }
+    }
+    return updated;
+}
+
+/* ------------------------------------------------------------------ A.4 */
+typedef struct {
+    uint64_t *keys;
+    int32_t *vals;
+    size_t cap, n;
+} orc_map;
+
+static void map_init(orc_map *m, size_t cap) {
+    m->cap = cap; m->n = 0;
+    m->keys = (uint64_t *)malloc(cap * sizeof(uint64_t));
+    m->vals = (int32_t *)malloc(cap * sizeof(int32_t));
+    memset(m->keys, 0xff, cap * sizeof(uint64_t));
+}
+static size_t map_slot(const orc_map *m, uint64_t k) {
+    uint64_t h = k * 0x9E3779B97F4A7C15ull;
+    size_t i = (size_t)(h >> 20) & (m->cap - 1);
+    while (m->keys[i] != UINT64_MAX && m->keys[i] != k) i = (i + 1) & (m->cap - 1);
+    return i;
+}
+static void map_grow(orc_map *m) {
+    orc_map n; map_init(&n, m->cap * 2);
+    for (size_t i = 0; i < m->cap; ++i)
+        if (m->keys[i] != UINT64_MAX) {
+            size_t s = map_slot(&n, m->keys[i]);
+            n.keys[s] = m->keys[i]; n.vals[s] = m->vals[i]; n.n++;
+        }
+    free(m->keys); free(m->vals); *m = n;
+}
+
+/*
+ * Serial marching cubes over cubes based at x in [0,nx-2], y in [0,ny-2], z in [0,nz-2]
+ * (x outer, z inner).  Vertices are shared through the edge key (x,y,z,axis) and
+ * numbered in first-seen order; triangles are (e[t0], e[t2], e[t1]).
+ * Outputs (capacity cap_v / cap_t rows; rows beyond capacity are counted, not written):
+ *   out_v   [V,3] f64 world position,   out_key [V,4] i32 (x,y,z,axis) local voxel coords,
+ *   out_c   [V,3] f64 colour in [0,1] (if color != NULL), out_t [T,3] i32.
+ * counts[0] = V, counts[1] = T.
+ */
+ORC_API void orc_extract_mesh(const float *tsdf, const float *weight, const float *color, int nx,
+                              int ny, int nz, int gz0, double voxel_length, const double *origin,
+                              double *out_v, int32_t *out_key, double *out_c, int64_t cap_v,
+                              int32_t *out_t, int64_t cap_t, int64_t *counts) {
+    const double half = voxel_length * 0.5;
+    orc_map map; map_init(&map, 1u << 16);
+    int64_t nv = 0, nt = 0;
+    for (int x = 0; x < nx - 1; ++x)
+        for (int y = 0; y < ny - 1; ++y)
+            for (int z = 0; z < nz - 1; ++z) {
+                int cube_index = 0, ok = 1;
+                float f[8]; size_t id[8];
+                for (int i = 0; i < 8; ++i) {
+                    id[i] = ((size_t)(x + orc_shift[i][0]) * ny + (y + orc_shift[i][1])) * nz + (z + orc_shift[i][2]);
+                    if (weight[id[i]] == 0.0f) { ok = 0; break; }
+                    f[i] = tsdf[id[i]];
+                    if (f[i] < 0.0f) cube_index |= (1 << i);
+                }
+                if (!ok || cube_index == 0 || cube_index == 255) continue;
+                const int em = orc_edge_table(cube_index);
+                int32_t e2v[12];
+                for (int e = 0; e < 12; ++e) {
+                    e2v[e] = -1;
+                    if (!(em & (1 << e))) continue;
+                    const int ex = x + orc_edge_shift[e][0], ey = y + orc_edge_shift[e][1],
+                              ez = z + orc_edge_shift[e][2], ax = orc_edge_shift[e][3];
+                    const uint64_t key = ((((uint64_t)ex * (uint64_t)ny + (uint64_t)ey) * (uint64_t)nz + (uint64_t)ez) << 2) | (uint64_t)ax;
+                    size_t s = map_slot(&map, key);
+                    if (map.keys[s] == UINT64_MAX) {
+                        if ((map.n + 1) * 2 > map.cap) { map_grow(&map); s = map_slot(&map, key); }
+                        map.keys[s] = key; map.vals[s] = (int32_t)nv; map.n++;
+                        const int i0 = orc_edge_to_vert[e][0], i1 = orc_edge_to_vert[e][1];
+                        const double f0 = fabs((double)f[i0]), f1 = fabs((double)f[i1]);
+                        if (nv < cap_v) {
+                            double pt[3] = {half + voxel_length * ex, half + voxel_length * ey,
+                                            half + voxel_length * (ez + gz0)};
+                            pt[ax] += f0 * voxel_length / (f0 + f1);
+                            for (int k = 0; k < 3; ++k) out_v[3 * nv + k] = pt[k] + origin[k];
+                            out_key[4 * nv + 0] = ex; out_key[4 * nv + 1] = ey;
+                            out_key[4 * nv + 2] = ez; out_key[4 * nv + 3] = ax;
+                            if (color && out_c)
+                                for (int k = 0; k < 3; ++k)
+                                    out_c[3 * nv + k] = ((f1 * (double)color[3 * id[i0] + k] + f0 * (double)color[3 * id[i1] + k]) / (f0 + f1)) / 255.0;
+                        }
+                        e2v[e] = (int32_t)nv++;
+                    } else {
+                        e2v[e] = map.vals[s];
+                    }
+                }
+                for (int i = 0; orc_tri_table[cube_index][i] != -1; i += 3) {
+                    if (nt < cap_t) {
+                        out_t[3 * nt + 0] = e2v[orc_tri_table[cube_index][i]];
+                        out_t[3 * nt + 1] = e2v[orc_tri_table[cube_index][i + 2]];
+                        out_t[3 * nt + 2] = e2v[orc_tri_table[cube_index][i + 1]];
+                    }
+                    ++nt;
+                }
+            }
+    free(map.keys); free(map.vals);
+    counts[0] = nv; counts[1] = nt;
+}
+
+/* ------------------------------------------------------------------ A.5 */
+static double tsdf_at(const float *tsdf, int ny, int nz, double voxel_length, const double *p) {
+    int idx[3]; double r[3];
+    for (int i = 0; i < 3; ++i) {
+        const double g = p[i] / voxel_length - 0.5;
+        idx[i] = (int)floor(g);
+        r[i] = g - (double)idx[i];
+    }
+#define TS(a, b, c) ((double)tsdf[((size_t)(idx[0] + a) * ny + (idx[1] + b)) * nz + (idx[2] + c)])
+    double t = 0;
+    t += (1 - r[0]) * (1 - r[1]) * (1 - r[2]) * TS(0, 0, 0);
+    t += (1 - r[0]) * (1 - r[1]) * r[2] * TS(0, 0, 1);
+    t += (1 - r[0]) * r[1] * (1 - r[2]) * TS(0, 1, 0);
+    t += (1 - r[0]) * r[1] * r[2] * TS(0, 1, 1);
+    t += r[0] * (1 - r[1]) * (1 - r[2]) * TS(1, 0, 0);
+    t += r[0] * (1 - r[1]) * r[2] * TS(1, 0, 1);
+    t += r[0] * r[1] * (1 - r[2]) * TS(1, 1, 0);
+    t += r[0] * r[1] * r[2] * TS(1, 1, 1);
+#undef TS
+    return t;
+}
+
+/*
+ * Surface points: interior voxels x,y,z in [1, n-2] (serial x,y,z order, then axis).
+ * Local coordinates are relative to the box (single-box volumes only: gz0 shifts the
+ * emitted position, the trilinear normal lookup stays inside the box).
+ * out_p [P,3] f64, out_n [P,3] f64 (unit normal, 0.99*voxel central difference of the
+ * trilinear TSDF at the point), out_c [P,3] f64 if color != NULL, out_key [P,4] i32.
+ */
+ORC_API int64_t orc_extract_points(const float *tsdf, const float *weight, const float *color,
+                                   int nx, int ny, int nz, int gz0, double voxel_length,
+                                   const double *origin, double *out_p, double *out_n,
+                                   double *out_c, int32_t *out_key, int64_t cap) {
+    const double half = voxel_length * 0.5;
+    const double half_gap = 0.99 * voxel_length;
+    const int n[3] = {nx, ny, nz};
+    int64_t np = 0;
+    for (int x = 1; x < nx - 1; ++x)
+        for (int y = 1; y < ny - 1; ++y)
+            for (int z = 1; z < nz - 1; ++z) {
+                const int idx0[3] = {x, y, z};
+                const size_t i0 = ((size_t)x * ny + y) * nz + z;
+                const float w0 = weight[i0], f0 = tsdf[i0];
+                if (!(w0 != 0.0f && f0 < 0.98f && f0 >= -0.98f)) continue;
+                const double p0[3] = {half + voxel_length * x, half + voxel_length * y, half + voxel_length * z};
+                for (int i = 0; i < 3; ++i) {
+                    int idx1[3] = {x, y, z};
+                    idx1[i] += 1;
+                    if (!(idx1[i] < n[i] - 1)) continue;
+                    const size_t i1 = ((size_t)idx1[0] * ny + idx1[1]) * nz + idx1[2];
+                    const float w1 = weight[i1], f1 = tsdf[i1];
+                    if (!(w1 != 0.0f && f1 < 0.98f && f1 >= -0.98f && f0 * f1 < 0)) continue;
+                    const float r0 = fabsf(f0), r1 = fabsf(f1);
+                    double p[3] = {p0[0], p0[1], p0[2]};
+                    const double p1i = p0[i] + voxel_length;
+                    p[i] = (p0[i] * r1 + p1i * r0) / (r0 + r1);
+                    if (np < cap) {
+                        for (int k = 0; k < 3; ++k) out_p[3 * np + k] = p[k] + origin[k];
+                        out_p[3 * np + 2] += voxel_length * gz0;
+                        if (color && out_c)
+                            for (int k = 0; k < 3; ++k)
+                                out_c[3 * np + k] = (((double)color[3 * i0 + k] * r1 + (double)color[3 * i1 + k] * r0) / (r0 + r1)) / 255.0;
+                        if (out_n) {
+                            double nn[3];
+                            for (int k = 0; k < 3; ++k) {
+                                double q0[3] = {p[0], p[1], p[2]}, q1[3] = {p[0], p[1], p[2]};
+                                q0[k] -= half_gap; q1[k] += half_gap;
+                                nn[k] = tsdf_at(tsdf, ny, nz, voxel_length, q1) - tsdf_at(tsdf, ny, nz, voxel_length, q0);
+                            }
+                            const double len = sqrt(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
+                            for (int k = 0; k < 3; ++k) out_n[3 * np + k] = len > 0 ? nn[k] / len : nn[k];
+                        }
+                        if (out_key) {
+                            out_key[4 * np + 0] = idx0[0]; out_key[4 * np + 1] = idx0[1];
+                            out_key[4 * np + 2] = idx0[2]; out_key[4 * np + 3] = i;
+                        }
+                    }
+                    ++np;
+                }
+            }
+    return np;
+}
+
+/* occupancy helper for the parity tests: number of voxels with weight != 0 */
+ORC_API int64_t orc_count_occupied(const float *weight, size_t n) {
+    int64_t c = 0;
+    for (size_t i = 0; i < n; ++i) c += weight[i] != 0.0f;
+    return c;
+}
