@@ -1,0 +1,83 @@
+// Shared host/device helpers of libbodyslam_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "bodyslam_b200.h"
+
+namespace bslam {
+
+void set_error(const char *fmt, ...);
+
+#define BSLAM_CHECK_ARG(cond, ...)              \
+    do {                                        \
+        if (!(cond)) {                          \
+            ::bslam::set_error(__VA_ARGS__);    \
+            return BSLAM_E_ARG;                 \
+        }                                       \
+    } while (0)
+
+#define BSLAM_CUDA(call)                                                                    \
+    do {                                                                                    \
+        cudaError_t e__ = (call);                                                           \
+        if (e__ != cudaSuccess) {                                                           \
+            ::bslam::set_error("%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),    \
+                               __FILE__, __LINE__);                                         \
+            return BSLAM_E_CUDA;                                                            \
+        }                                                                                   \
+    } while (0)
+
+#define BSLAM_LAUNCH_CHECK() BSLAM_CUDA(cudaGetLastError())
+
+constexpr int kBrick = BSLAM_BRICK;                 // 8
+constexpr int kBrickVox = kBrick * kBrick * kBrick; // 512
+constexpr int kNumSMs = 148;                        // B200
+
+// Device view of a brick-ordered volume.  Brick b = (bz*nby + by)*nbx + bx holds 512 float2
+// {tsdf, weight}; in-brick index = lz*64 + lx*8 + ly  (a warp owns 32 consecutive (lx,ly)
+// columns of one z layer -> one 256-byte line per access).
+struct VolView {
+    float2 *vox;
+    float *color;        // optional: per brick 3 planes of 512 f32 (r, g, b)
+    uint8_t *flags;      // per brick: 1 once any voxel of the brick was updated
+    int nx, ny, nz, gz0; // logical box
+    int nbx, nby, nbz;   // bricks per axis (ceil)
+    float vl, half, trunc, trunc_inv;
+    double ox, oy, oz;
+};
+
+__host__ __device__ inline int64_t brick_count(const VolView &v) {
+    return (int64_t)v.nbx * v.nby * v.nbz;
+}
+
+__device__ __forceinline__ int64_t voxel_slot(const VolView &v, int x, int y, int z) {
+    const int bx = x >> 3, by = y >> 3, bz = z >> 3;
+    const int64_t b = ((int64_t)bz * v.nby + by) * v.nbx + bx;
+    return b * kBrickVox + ((z & 7) << 6) + ((x & 7) << 3) + (y & 7);
+}
+
+} // namespace bslam
+
+// host-side handle
+struct bslam_volume {
+    bslam::VolView v;
+    int device;
+    int with_color;
+    int owns_storage;
+    void *storage;
+    size_t storage_bytes;
+    double voxel_length_d, sdf_trunc_d;
+    // extraction scratch (lazily sized by brick count)
+    void *mc_scratch;
+    size_t mc_scratch_bytes;
+    // integrate scratch: active-brick list + counters
+    void *int_scratch;
+    size_t int_scratch_bytes;
+    // optional per-launch timing of the dominant kernel (bslam_tsdf_profile)
+    int prof_enabled, prof_n;
+    cudaEvent_t prof_ev[2 * 64];
+    double prof_ms_accum;
+    long long prof_launches_accum;
+};

@@ -1,0 +1,455 @@
+// K4 -- surface extraction (marching cubes + point cloud) for sm_100a.
+//
+// Semantics: Open3D extract_triangle_mesh / extract_point_cloud as reached from
+// TSDF.extract_mesh / TSDF.extract_pcd (N/3DM/tsdf.py:39-43); restated in SURVEY.md
+// Appendix A.4/A.5 and checked against oracle/o3d_oracle.c.
+//
+// One CTA per 8^3 brick (512 threads, one per voxel).  Bricks never touched by integration
+// (flag byte 0) exit without reading the volume.  Compaction is count -> prefix sum -> emit:
+//   * warp ballots give, per 32-voxel chunk and axis, the mask of edges that own a vertex;
+//     popc prefixes of the 48 mask words number the vertices inside a brick;
+//   * a prefix sum over bricks gives each brick's vertex / triangle base;
+//   * triangle corners are resolved to vertex ids with  base[b'] + prefix[b'][w] + popc(mask & lt)
+//     of the OWNING brick b' -- no hash map, no atomics, deterministic output order.
+#include <math.h>
+
+#include "bslam_common.cuh"
+#include "mc_tables.cuh"
+
+namespace bslam {
+
+constexpr int kMaskWordsPerBrick = 48; // 16 chunks of 32 voxels x 3 axes
+constexpr int kR = 10;                 // staged region edge: voxels -1 .. 8 of the brick
+
+struct McScratch {
+    uint32_t *vmask;     // [nb][48]
+    uint16_t *vprefix;   // [nb][48] exclusive popc prefix inside the brick
+    uint32_t *nvert;     // [nb]
+    uint32_t *ntri;      // [nb]
+    uint32_t *vbase;     // [nb] exclusive prefix over bricks
+    uint32_t *tbase;     // [nb]
+    unsigned long long *totals; // [2]
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static size_t mc_scratch_bytes(size_t nb) {
+    return align_up(nb * kMaskWordsPerBrick * 4, 256) + align_up(nb * kMaskWordsPerBrick * 2, 256) + 4 * align_up(nb * 4, 256) + 256;
+}
+
+static McScratch carve_mc(void *p0, size_t nb) {
+    char *p = (char *)p0;
+    McScratch s;
+    s.vmask = (uint32_t *)p; p += align_up(nb * kMaskWordsPerBrick * 4, 256);
+    s.vprefix = (uint16_t *)p; p += align_up(nb * kMaskWordsPerBrick * 2, 256);
+    s.nvert = (uint32_t *)p; p += align_up(nb * 4, 256);
+    s.ntri = (uint32_t *)p; p += align_up(nb * 4, 256);
+    s.vbase = (uint32_t *)p; p += align_up(nb * 4, 256);
+    s.tbase = (uint32_t *)p; p += align_up(nb * 4, 256);
+    s.totals = (unsigned long long *)p;
+    return s;
+}
+
+// {tsdf, weight} of local voxel (x,y,z); outside the box -> weight 0; z = -1 / nz -> halo planes
+__device__ __forceinline__ float2 fetch_voxel(const VolView &v, const float2 *halo_lo, const float2 *halo_hi, int x, int y, int z) {
+    if (x < 0 || y < 0 || x >= v.nx || y >= v.ny || z < -1 || z > v.nz) return make_float2(0.f, 0.f);
+    if (z == -1) return halo_lo ? halo_lo[(int64_t)x * v.ny + y] : make_float2(0.f, 0.f);
+    if (z == v.nz) return halo_hi ? halo_hi[(int64_t)x * v.ny + y] : make_float2(0.f, 0.f);
+    return v.vox[voxel_slot(v, x, y, z)];
+}
+
+struct BrickClass {
+    bool cube_valid;
+    int cube_index;
+    unsigned int vbits; // bit a: the edge from this voxel towards +axis a owns a vertex
+};
+
+__device__ __forceinline__ int ridx(int rx, int ry, int rz) { return (rz * kR + rx) * kR + ry; }
+
+// Stage the 10^3 neighbourhood of brick (bx,by,bz) and classify the calling thread's voxel.
+__device__ __forceinline__ BrickClass classify_brick(const VolView &v, const float2 *halo_lo, const float2 *halo_hi, int bx, int by, int bz,
+                                                     float *s_t, uint8_t *s_ok, uint8_t *s_cv) {
+    const int tid = threadIdx.x;
+    for (int i = tid; i < kR * kR * kR; i += kBrickVox) {
+        const int ry = i % kR, rx = (i / kR) % kR, rz = i / (kR * kR);
+        const float2 t = fetch_voxel(v, halo_lo, halo_hi, bx * 8 - 1 + rx, by * 8 - 1 + ry, bz * 8 - 1 + rz);
+        s_t[i] = t.x;
+        s_ok[i] = t.y != 0.0f;
+    }
+    __syncthreads();
+    // cube validity for the 9^3 cubes based at region coords [0,9)^3
+    for (int i = tid; i < 9 * 9 * 9; i += kBrickVox) {
+        const int cy = i % 9, cx = (i / 9) % 9, cz = i / 81;
+        uint8_t ok = 1;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) ok &= s_ok[ridx(cx + ((k & 1) ? 1 : 0), cy + ((k & 2) ? 1 : 0), cz + ((k & 4) ? 1 : 0))];
+        s_cv[(cz * 9 + cx) * 9 + cy] = ok;
+    }
+    __syncthreads();
+    const int ly = tid & 7, lx = (tid >> 3) & 7, lz = tid >> 6;
+    const int rx = lx + 1, ry = ly + 1, rz = lz + 1;
+    BrickClass c;
+    c.cube_valid = s_cv[(rz * 9 + rx) * 9 + ry] != 0 && (bz * 8 + lz < v.nz); // cubes based on the halo_hi plane belong to the slab above
+    c.cube_index = 0;
+    if (c.cube_valid) {
+        // Open3D corner order: (0,0,0),(1,0,0),(1,1,0),(0,1,0),(0,0,1),(1,0,1),(1,1,1),(0,1,1)
+        const int sx[8] = {0, 1, 1, 0, 0, 1, 1, 0}, sy[8] = {0, 0, 1, 1, 0, 0, 1, 1}, sz[8] = {0, 0, 0, 0, 1, 1, 1, 1};
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (s_t[ridx(rx + sx[k], ry + sy[k], rz + sz[k])] < 0.0f) c.cube_index |= 1 << k;
+    }
+    c.vbits = 0;
+    const bool own = (bx * 8 + lx < v.nx) && (by * 8 + ly < v.ny) && (bz * 8 + lz < v.nz) && s_ok[ridx(rx, ry, rz)];
+    if (own) {
+        const bool neg0 = s_t[ridx(rx, ry, rz)] < 0.0f;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const int nx_ = rx + (a == 0), ny_ = ry + (a == 1), nz_ = rz + (a == 2);
+            if (!s_ok[ridx(nx_, ny_, nz_)]) continue;
+            if ((s_t[ridx(nx_, ny_, nz_)] < 0.0f) == neg0) continue;
+            // the 4 cubes sharing this edge: base = voxel - {0,1} along the two other axes
+            bool any = false;
+#pragma unroll
+            for (int d = 0; d < 4; ++d) {
+                int qx = rx, qy = ry, qz = rz;
+                const int d0 = d & 1, d1 = d >> 1;
+                if (a == 0) { qy -= d0; qz -= d1; }
+                if (a == 1) { qx -= d0; qz -= d1; }
+                if (a == 2) { qx -= d0; qy -= d1; }
+                // cubes based on the halo_hi plane do not exist for this slab's vertices either:
+                // they can only be reached from voxels of that plane, which are not owned here
+                any |= s_cv[(qz * 9 + qx) * 9 + qy] != 0;
+            }
+            if (any) c.vbits |= 1u << a;
+        }
+    }
+    return c;
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(kBrickVox) mc_brick_kernel(const VolView v, double vld, const float2 *halo_lo, const float2 *halo_hi, McScratch sc,
+                                                              float *vertices, int32_t *keys, float *colors, int64_t cap_v,
+                                                              int32_t *tris, int64_t cap_t) {
+    __shared__ float s_t[kR * kR * kR];
+    __shared__ uint8_t s_ok[kR * kR * kR];
+    __shared__ uint8_t s_cv[9 * 9 * 9];
+    __shared__ uint32_t s_mask[kMaskWordsPerBrick];
+    __shared__ uint32_t s_pref[kMaskWordsPerBrick];
+    __shared__ uint32_t s_wtri[16];
+    const int64_t b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (!v.flags[b]) {
+        if (!EMIT && tid == 0) { sc.nvert[b] = 0; sc.ntri[b] = 0; }
+        return;
+    }
+    if (EMIT && sc.nvert[b] == 0 && sc.ntri[b] == 0) return;
+    const int bx = (int)(b % v.nbx), by = (int)((b / v.nbx) % v.nby), bz = (int)(b / ((int64_t)v.nbx * v.nby));
+    const BrickClass c = classify_brick(v, halo_lo, halo_hi, bx, by, bz, s_t, s_ok, s_cv);
+
+    // vertex masks: word 3*chunk + axis, chunk == warp id (in-brick index == tid)
+    unsigned int bal[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        bal[a] = __ballot_sync(0xffffffffu, (c.vbits >> a) & 1u);
+        if (lane == 0) s_mask[3 * wid + a] = bal[a];
+    }
+    int ntri = c.cube_valid ? (int)kNumTris[c.cube_index] : 0;
+    // block scan of triangle counts (exclusive) -- warp scan + warp totals
+    int inc = ntri;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_wtri[wid] = inc;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t acc = 0;
+        for (int w = 0; w < kMaskWordsPerBrick; ++w) { s_pref[w] = acc; acc += __popc(s_mask[w]); }
+        uint32_t tacc = 0;
+        for (int w = 0; w < 16; ++w) { const uint32_t t = s_wtri[w]; s_wtri[w] = tacc; tacc += t; }
+        if (!EMIT) { sc.nvert[b] = acc; sc.ntri[b] = tacc; }
+    }
+    __syncthreads();
+    if (!EMIT) {
+        if (tid < kMaskWordsPerBrick) {
+            sc.vmask[b * kMaskWordsPerBrick + tid] = s_mask[tid];
+            sc.vprefix[b * kMaskWordsPerBrick + tid] = (uint16_t)s_pref[tid];
+        }
+        return;
+    }
+    // ---------------- emit vertices
+    const int ly = tid & 7, lx = (tid >> 3) & 7, lz = tid >> 6;
+    const int X = bx * 8 + lx, Y = by * 8 + ly, Z = bz * 8 + lz;
+    const uint32_t vb = sc.vbase[b];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        if (!((c.vbits >> a) & 1u)) continue;
+        const int64_t id = (int64_t)vb + s_pref[3 * wid + a] + __popc(bal[a] & ((1u << lane) - 1u));
+        if (id >= cap_v) continue;
+        const int rx = lx + 1, ry = ly + 1, rz = lz + 1;
+        const double f0 = fabs((double)s_t[ridx(rx, ry, rz)]);
+        const double f1 = fabs((double)s_t[ridx(rx + (a == 0), ry + (a == 1), rz + (a == 2))]);
+        // Open3D: pt = half + vl * (x,y,z) (f64); pt[axis] += f0 * vl / (f0 + f1); + origin
+        double pt[3] = {0.5 * vld + vld * X, 0.5 * vld + vld * Y, 0.5 * vld + vld * (Z + v.gz0)};
+        pt[a] += f0 * vld / (f0 + f1);
+        vertices[3 * id + 0] = (float)(pt[0] + v.ox);
+        vertices[3 * id + 1] = (float)(pt[1] + v.oy);
+        vertices[3 * id + 2] = (float)(pt[2] + v.oz);
+        if (keys) { keys[4 * id + 0] = X; keys[4 * id + 1] = Y; keys[4 * id + 2] = Z; keys[4 * id + 3] = a; }
+        if (colors && v.color) {
+            const int64_t s0 = voxel_slot(v, X, Y, Z);
+            const int X1 = X + (a == 0), Y1 = Y + (a == 1), Z1 = Z + (a == 2);
+            // colour of a voxel on the halo_hi plane is not available: reuse the owner's colour
+            const int64_t s1 = (Z1 < v.nz) ? voxel_slot(v, X1, Y1, Z1) : s0;
+            for (int k = 0; k < 3; ++k) {
+                const double c0 = v.color[(s0 / kBrickVox) * (3 * kBrickVox) + k * kBrickVox + (s0 % kBrickVox)];
+                const double c1 = v.color[(s1 / kBrickVox) * (3 * kBrickVox) + k * kBrickVox + (s1 % kBrickVox)];
+                colors[3 * id + k] = (float)(((f1 * c0 + f0 * c1) / (f0 + f1)) / 255.0);
+            }
+        }
+    }
+    // ---------------- emit triangles
+    if (ntri) {
+        int64_t t_out = (int64_t)sc.tbase[b] + s_wtri[wid] + (inc - ntri);
+        const int8_t *row = kTriTable + c.cube_index * 16;
+        for (int i = 0; i < ntri; ++i, ++t_out) {
+            if (t_out >= cap_t) break;
+            int32_t ids[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int e = row[3 * i + k];
+                const int ox_ = X + kEdgeShift[4 * e + 0], oy_ = Y + kEdgeShift[4 * e + 1], oz_ = Z + kEdgeShift[4 * e + 2];
+                const int ax = kEdgeShift[4 * e + 3];
+                if (oz_ >= v.nz) { // owned by the first plane of the slab above
+                    ids[k] = -(1 + (ox_ * v.ny + oy_) * 4 + ax);
+                    continue;
+                }
+                const int64_t ob = ((int64_t)(oz_ >> 3) * v.nby + (oy_ >> 3)) * v.nbx + (ox_ >> 3);
+                const int in = ((oz_ & 7) << 6) + ((ox_ & 7) << 3) + (oy_ & 7);
+                const int w = 3 * (in >> 5) + ax;
+                const uint32_t m = sc.vmask[ob * kMaskWordsPerBrick + w];
+                ids[k] = (int32_t)(sc.vbase[ob] + sc.vprefix[ob * kMaskWordsPerBrick + w] + __popc(m & ((1u << (in & 31)) - 1u)));
+            }
+            // Open3D pushes (e[t0], e[t2], e[t1])
+            tris[3 * t_out + 0] = ids[0];
+            tris[3 * t_out + 1] = ids[2];
+            tris[3 * t_out + 2] = ids[1];
+        }
+    }
+}
+
+// exclusive prefix sums over bricks (single CTA; nb <= a few million)
+__global__ void __launch_bounds__(1024) brick_scan_kernel(const uint32_t *a, const uint32_t *b, uint32_t *abase, uint32_t *bbase, int64_t n,
+                                                          unsigned long long *totals) {
+    __shared__ unsigned long long sa[1024], sb[1024];
+    __shared__ unsigned long long ca, cb;
+    if (threadIdx.x == 0) { ca = 0; cb = 0; }
+    __syncthreads();
+    for (int64_t base = 0; base < n; base += 1024) {
+        const int64_t i = base + threadIdx.x;
+        const unsigned long long va = (i < n) ? a[i] : 0, vb = (i < n && b) ? b[i] : 0;
+        sa[threadIdx.x] = va; sb[threadIdx.x] = vb;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            const unsigned long long ta = (threadIdx.x >= o) ? sa[threadIdx.x - o] : 0, tb = (threadIdx.x >= o) ? sb[threadIdx.x - o] : 0;
+            __syncthreads();
+            sa[threadIdx.x] += ta; sb[threadIdx.x] += tb;
+            __syncthreads();
+        }
+        if (i < n) {
+            abase[i] = (uint32_t)(ca + sa[threadIdx.x] - va);
+            if (b) bbase[i] = (uint32_t)(cb + sb[threadIdx.x] - vb);
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) { ca += sa[1023]; cb += sb[1023]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { totals[0] = ca; totals[1] = cb; }
+}
+
+// ---------------------------------------------------------------- surface points (A.5)
+__device__ __forceinline__ bool pt_ok(float2 t) { return t.y != 0.0f && t.x < 0.98f && t.x >= -0.98f; }
+
+__device__ double tsdf_at(const VolView &v, double vl, const double *p) {
+    int idx[3]; double r[3];
+    for (int i = 0; i < 3; ++i) {
+        const double g = p[i] / vl - 0.5;
+        idx[i] = (int)floor(g);
+        r[i] = g - (double)idx[i];
+    }
+    double t = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { // Open3D term order: (0,0,0),(0,0,1),(0,1,0),(0,1,1),(1,0,0),...
+        const int a = (k >> 2) & 1, b = (k >> 1) & 1, c = k & 1;
+        const double wgt = (a ? r[0] : 1 - r[0]) * (b ? r[1] : 1 - r[1]) * (c ? r[2] : 1 - r[2]);
+        t += wgt * (double)v.vox[voxel_slot(v, idx[0] + a, idx[1] + b, idx[2] + c)].x;
+    }
+    return t;
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(kBrickVox) points_brick_kernel(const VolView v, double vl, McScratch sc, float *points, float *normals,
+                                                                  float *colors, int32_t *keys, int64_t cap) {
+    __shared__ uint32_t s_w[16];
+    const int64_t b = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (!v.flags[b]) {
+        if (!EMIT && tid == 0) sc.nvert[b] = 0;
+        return;
+    }
+    if (EMIT && sc.nvert[b] == 0) return;
+    const int bx = (int)(b % v.nbx), by = (int)((b / v.nbx) % v.nby), bz = (int)(b / ((int64_t)v.nbx * v.nby));
+    const int ly = tid & 7, lx = (tid >> 3) & 7, lz = tid >> 6;
+    const int X = bx * 8 + lx, Y = by * 8 + ly, Z = bz * 8 + lz;
+    const int n[3] = {v.nx, v.ny, v.nz};
+    unsigned int bits = 0;
+    float2 t0 = make_float2(0.f, 0.f), t1[3];
+    if (X >= 1 && Y >= 1 && Z >= 1 && X < v.nx - 1 && Y < v.ny - 1 && Z < v.nz - 1) {
+        t0 = v.vox[b * kBrickVox + tid];
+        if (pt_ok(t0)) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const int c1[3] = {X + (a == 0), Y + (a == 1), Z + (a == 2)};
+                if (!(c1[a] < n[a] - 1)) continue;
+                t1[a] = v.vox[voxel_slot(v, c1[0], c1[1], c1[2])];
+                if (pt_ok(t1[a]) && t0.x * t1[a].x < 0) bits |= 1u << a;
+            }
+        }
+    }
+    const int cnt = __popc(bits);
+    int inc = cnt;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_w[wid] = inc;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t acc = 0;
+        for (int w = 0; w < 16; ++w) { const uint32_t t = s_w[w]; s_w[w] = acc; acc += t; }
+        if (!EMIT) sc.nvert[b] = acc;
+    }
+    __syncthreads();
+    if (!EMIT || !cnt) return;
+    int64_t o = (int64_t)sc.vbase[b] + s_w[wid] + (inc - cnt);
+    const double half = vl * 0.5, half_gap = 0.99 * vl;
+    const double p0[3] = {half + vl * X, half + vl * Y, half + vl * Z};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        if (!((bits >> a) & 1u)) continue;
+        if (o < cap) {
+            const float r0 = fabsf(t0.x), r1 = fabsf(t1[a].x);
+            double p[3] = {p0[0], p0[1], p0[2]};
+            p[a] = (p0[a] * r1 + (p0[a] + vl) * r0) / (r0 + r1);
+            points[3 * o + 0] = (float)(p[0] + v.ox);
+            points[3 * o + 1] = (float)(p[1] + v.oy);
+            points[3 * o + 2] = (float)(p[2] + v.oz + vl * v.gz0);
+            if (keys) { keys[4 * o + 0] = X; keys[4 * o + 1] = Y; keys[4 * o + 2] = Z; keys[4 * o + 3] = a; }
+            if (normals) {
+                double nn[3];
+                for (int k = 0; k < 3; ++k) {
+                    double q0[3] = {p[0], p[1], p[2]}, q1[3] = {p[0], p[1], p[2]};
+                    q0[k] -= half_gap; q1[k] += half_gap;
+                    nn[k] = tsdf_at(v, vl, q1) - tsdf_at(v, vl, q0);
+                }
+                const double len = sqrt(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
+                for (int k = 0; k < 3; ++k) normals[3 * o + k] = (float)(len > 0 ? nn[k] / len : nn[k]);
+            }
+            if (colors && v.color) {
+                const int64_t s0 = b * kBrickVox + tid;
+                const int64_t s1 = voxel_slot(v, X + (a == 0), Y + (a == 1), Z + (a == 2));
+                for (int k = 0; k < 3; ++k) {
+                    const double c0 = v.color[(s0 / kBrickVox) * (3 * kBrickVox) + k * kBrickVox + (s0 % kBrickVox)];
+                    const double c1 = v.color[(s1 / kBrickVox) * (3 * kBrickVox) + k * kBrickVox + (s1 % kBrickVox)];
+                    colors[3 * o + k] = (float)(((c0 * r1 + c1 * r0) / (r0 + r1)) / 255.0);
+                }
+            }
+        }
+        ++o;
+    }
+}
+
+static int ensure_mc_scratch(bslam_volume *vol) {
+    const size_t nb = (size_t)brick_count(vol->v);
+    const size_t need = mc_scratch_bytes(nb);
+    if (vol->mc_scratch && vol->mc_scratch_bytes >= need) return BSLAM_OK;
+    if (vol->mc_scratch) cudaFree(vol->mc_scratch);
+    vol->mc_scratch = nullptr;
+    BSLAM_CUDA(cudaMalloc(&vol->mc_scratch, need));
+    vol->mc_scratch_bytes = need;
+    return BSLAM_OK;
+}
+
+} // namespace bslam
+
+using namespace bslam;
+
+extern "C" {
+
+int bslam_mc_count(bslam_volume *vol, const float *d_halo_lo, const float *d_halo_hi, int64_t *h_counts, bslam_stream_t stream) {
+    BSLAM_CHECK_ARG(vol && h_counts, "bslam_mc_count: NULL argument");
+    BSLAM_CUDA(cudaSetDevice(vol->device));
+    int rc = ensure_mc_scratch(vol);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t nb = brick_count(vol->v);
+    const McScratch sc = carve_mc(vol->mc_scratch, (size_t)nb);
+    mc_brick_kernel<false><<<(unsigned)nb, kBrickVox, 0, st>>>(vol->v, vol->voxel_length_d, (const float2 *)d_halo_lo, (const float2 *)d_halo_hi, sc, nullptr, nullptr,
+                                                                nullptr, 0, nullptr, 0);
+    BSLAM_LAUNCH_CHECK();
+    brick_scan_kernel<<<1, 1024, 0, st>>>(sc.nvert, sc.ntri, sc.vbase, sc.tbase, nb, sc.totals);
+    BSLAM_LAUNCH_CHECK();
+    unsigned long long tot[2];
+    BSLAM_CUDA(cudaMemcpyAsync(tot, sc.totals, 16, cudaMemcpyDeviceToHost, st));
+    BSLAM_CUDA(cudaStreamSynchronize(st));
+    h_counts[0] = (int64_t)tot[0];
+    h_counts[1] = (int64_t)tot[1];
+    return BSLAM_OK;
+}
+
+int bslam_mc_emit(bslam_volume *vol, const float *d_halo_lo, const float *d_halo_hi, float *d_vertices, int32_t *d_keys, float *d_colors,
+                  int64_t cap_v, int32_t *d_tri, int64_t cap_t, bslam_stream_t stream) {
+    BSLAM_CHECK_ARG(vol && vol->mc_scratch, "bslam_mc_emit: call bslam_mc_count first");
+    BSLAM_CHECK_ARG((d_vertices || cap_v == 0) && (d_tri || cap_t == 0), "bslam_mc_emit: NULL output");
+    BSLAM_CUDA(cudaSetDevice(vol->device));
+    const int64_t nb = brick_count(vol->v);
+    const McScratch sc = carve_mc(vol->mc_scratch, (size_t)nb);
+    mc_brick_kernel<true><<<(unsigned)nb, kBrickVox, 0, (cudaStream_t)stream>>>(vol->v, vol->voxel_length_d, (const float2 *)d_halo_lo, (const float2 *)d_halo_hi, sc,
+                                                                                 d_vertices, d_keys, d_colors, cap_v, d_tri, cap_t);
+    BSLAM_LAUNCH_CHECK();
+    return BSLAM_OK;
+}
+
+int bslam_points_count(bslam_volume *vol, int64_t *h_count, bslam_stream_t stream) {
+    BSLAM_CHECK_ARG(vol && h_count, "bslam_points_count: NULL argument");
+    BSLAM_CHECK_ARG(vol->v.gz0 == 0, "bslam_points_count: single-box volumes only (gz0 must be 0)");
+    BSLAM_CUDA(cudaSetDevice(vol->device));
+    int rc = ensure_mc_scratch(vol);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t nb = brick_count(vol->v);
+    const McScratch sc = carve_mc(vol->mc_scratch, (size_t)nb);
+    points_brick_kernel<false><<<(unsigned)nb, kBrickVox, 0, st>>>(vol->v, vol->voxel_length_d, sc, nullptr, nullptr, nullptr, nullptr, 0);
+    BSLAM_LAUNCH_CHECK();
+    brick_scan_kernel<<<1, 1024, 0, st>>>(sc.nvert, nullptr, sc.vbase, nullptr, nb, sc.totals);
+    BSLAM_LAUNCH_CHECK();
+    unsigned long long tot[2];
+    BSLAM_CUDA(cudaMemcpyAsync(tot, sc.totals, 16, cudaMemcpyDeviceToHost, st));
+    BSLAM_CUDA(cudaStreamSynchronize(st));
+    *h_count = (int64_t)tot[0];
+    return BSLAM_OK;
+}
+
+int bslam_points_emit(bslam_volume *vol, float *d_points, float *d_normals, float *d_colors, int32_t *d_keys, int64_t cap, bslam_stream_t stream) {
+    BSLAM_CHECK_ARG(vol && vol->mc_scratch, "bslam_points_emit: call bslam_points_count first");
+    BSLAM_CHECK_ARG(d_points || cap == 0, "bslam_points_emit: NULL output");
+    BSLAM_CUDA(cudaSetDevice(vol->device));
+    const int64_t nb = brick_count(vol->v);
+    const McScratch sc = carve_mc(vol->mc_scratch, (size_t)nb);
+    points_brick_kernel<true><<<(unsigned)nb, kBrickVox, 0, (cudaStream_t)stream>>>(vol->v, vol->voxel_length_d, sc, d_points, d_normals, d_colors,
+                                                                                     d_keys, cap);
+    BSLAM_LAUNCH_CHECK();
+    return BSLAM_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,587 @@
+// K1 (metric scaling + colorize), a4 (3DM depth scaling) and K2 (back-projection + SE(3))
+// for sm_100a.  All three are pure HBM streaming: 128-bit loads/stores, grids sized in
+// multiples of the SM count, no tensor cores (nothing here is a contraction).
+//
+// Semantics (checked against oracle/mdem.py and oracle/o3d_oracle.c):
+//   K1  R/examples/depth_estimation/depth_map_scaling.py:12-45  (colorize)
+//       + ZoeDepth infer_pil tail (R/src/depth_estimation/interface.py:61)
+//   a4  N/3DM/slam_utils.py:212-220,231-233
+//   K2  N/3DM/scaling_system.py:72-77, N/3DM/mapping_module.py:37,41
+#include <math.h>
+
+#include "bslam_common.cuh"
+
+namespace bslam {
+
+constexpr int kBins = 65536;
+
+// per-image workspace: [hist u32 x 65536][index table u8 x 65536][stats]
+struct ImgStats {
+    double vmin, vmax;
+    unsigned long long n_valid;
+    unsigned int vmin_u, vmax_u; // min / max valid value (minmax path)
+};
+constexpr size_t kWsPerImage = kBins * 4 + kBins + 256;
+
+__device__ __forceinline__ unsigned int *ws_hist(void *ws, int b) { return (unsigned int *)((char *)ws + (size_t)b * kWsPerImage); }
+__device__ __forceinline__ uint8_t *ws_table(void *ws, int b) { return (uint8_t *)((char *)ws + (size_t)b * kWsPerImage + kBins * 4); }
+__device__ __forceinline__ ImgStats *ws_stats(void *ws, int b) { return (ImgStats *)((char *)ws + (size_t)b * kWsPerImage + kBins * 4 + kBins); }
+
+__device__ __forceinline__ unsigned int to_u16_sat(float m, float scale_mul) {
+    // numpy: (metres * 256).astype(uint16) -- f32 multiply, truncation toward zero.
+    const float s = m * scale_mul;
+    return (unsigned int)fminf(fmaxf(truncf(s), 0.0f), 65535.0f); // NaN -> 0
+}
+
+// ---------------------------------------------------------------- K1 pass A: scale + histogram
+// Each block owns kPxPerBlock consecutive pixels of one image, keeps them in registers,
+// histograms into a shared window anchored at the block minimum and flushes the non-empty bins.
+constexpr int kHistThreads = 256;
+constexpr int kPxPerThread = 16;
+constexpr int kPxPerBlock = kHistThreads * kPxPerThread;
+constexpr int kWindow = 4096;
+
+template <bool FROM_FLOAT>
+__global__ void __launch_bounds__(kHistThreads) scale_hist_kernel(const float *__restrict__ depth_m, const uint16_t *__restrict__ u16_in,
+                                                                   uint16_t *__restrict__ u16_out, int64_t n_per_image, float scale_mul,
+                                                                   int has_invalid, unsigned int invalid_val, void *ws) {
+    __shared__ unsigned int s_hist[kWindow];
+    __shared__ unsigned int s_min;
+    const int b = blockIdx.y;
+    const int64_t start = (int64_t)blockIdx.x * kPxPerBlock;
+    unsigned int *hist = ws_hist(ws, b);
+    for (int i = threadIdx.x; i < kWindow; i += kHistThreads) s_hist[i] = 0;
+    if (threadIdx.x == 0) s_min = 0xffffffffu;
+    __syncthreads();
+
+    unsigned int val[kPxPerThread];
+    unsigned int tmin = 0xffffffffu;
+    const int64_t img_off = (int64_t)b * n_per_image;
+    // thread t handles 4 groups of 4 consecutive pixels, groups strided by 1024 -> 16-byte accesses
+#pragma unroll
+    for (int g = 0; g < kPxPerThread / 4; ++g) {
+        const int64_t p = start + (int64_t)g * (kHistThreads * 4) + threadIdx.x * 4;
+        if (p + 3 < n_per_image && ((img_off + p) & 3) == 0) {
+            if (FROM_FLOAT) {
+                const float4 d = *reinterpret_cast<const float4 *>(depth_m + img_off + p);
+                val[4 * g + 0] = to_u16_sat(d.x, scale_mul); val[4 * g + 1] = to_u16_sat(d.y, scale_mul);
+                val[4 * g + 2] = to_u16_sat(d.z, scale_mul); val[4 * g + 3] = to_u16_sat(d.w, scale_mul);
+                if (u16_out) {
+                    ushort4 o = make_ushort4((unsigned short)val[4 * g], (unsigned short)val[4 * g + 1],
+                                             (unsigned short)val[4 * g + 2], (unsigned short)val[4 * g + 3]);
+                    *reinterpret_cast<ushort4 *>(u16_out + img_off + p) = o;
+                }
+            } else {
+                const ushort4 d = *reinterpret_cast<const ushort4 *>(u16_in + img_off + p);
+                val[4 * g + 0] = d.x; val[4 * g + 1] = d.y; val[4 * g + 2] = d.z; val[4 * g + 3] = d.w;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                unsigned int x = 0xffffffffu; // out of range marker
+                if (p + j < n_per_image) {
+                    if (FROM_FLOAT) {
+                        x = to_u16_sat(depth_m[img_off + p + j], scale_mul);
+                        if (u16_out) u16_out[img_off + p + j] = (unsigned short)x;
+                    } else {
+                        x = u16_in[img_off + p + j];
+                    }
+                }
+                val[4 * g + j] = x;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            unsigned int &x = val[4 * g + j];
+            if (x != 0xffffffffu && has_invalid && x == invalid_val) x = 0xffffffffu;
+            tmin = min(tmin, x);
+        }
+    }
+    for (int o = 16; o; o >>= 1) tmin = min(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
+    if ((threadIdx.x & 31) == 0 && tmin != 0xffffffffu) atomicMin(&s_min, tmin);
+    __syncthreads();
+    const unsigned int base = s_min;
+    if (base == 0xffffffffu) return; // no valid pixel in this block
+    // run-length merge inside the thread, then shared (window) or global atomics
+    unsigned int run_v = 0xffffffffu, run_n = 0;
+#pragma unroll
+    for (int i = 0; i <= kPxPerThread; ++i) {
+        const unsigned int x = (i < kPxPerThread) ? val[i] : 0xffffffffu;
+        if (x == run_v && x != 0xffffffffu) {
+            ++run_n;
+        } else {
+            if (run_n) {
+                const unsigned int rel = run_v - base;
+                if (rel < kWindow) atomicAdd(&s_hist[rel], run_n);
+                else atomicAdd(&hist[run_v], run_n);
+            }
+            run_v = x; run_n = (x != 0xffffffffu) ? 1u : 0u;
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kWindow; i += kHistThreads) {
+        const unsigned int c = s_hist[i];
+        if (c) atomicAdd(&hist[base + i], c);
+    }
+}
+
+// ---------------------------------------------------------------- K1 pass B: order statistics + index table
+__device__ double numpy_lerp(double a, double b, double t) {
+    // numpy.lib._function_base_impl._lerp
+    const double diff = b - a;
+    double r = a + diff * t;
+    if (t >= 0.5) r = b - diff * (1.0 - t);
+    return r;
+}
+
+// mode 0: percentile colorize table; mode 1: min-max uint8 table; mode 2: median only
+__global__ void __launch_bounds__(1024) stats_table_kernel(void *ws, double p_lo, double p_hi, const double *vmin_vmax_override /*device*/,
+                                                           double *vmin_vmax_out, double *median_out, int mode,
+                                                           const uint8_t *table_override) {
+    __shared__ unsigned long long s_part[1024];
+    __shared__ double s_vals[4];
+    __shared__ unsigned int s_mm[2];
+    const int b = blockIdx.x, t = threadIdx.x;
+    const unsigned int *hist = ws_hist(ws, b);
+    uint8_t *table = ws_table(ws, b);
+    ImgStats *st = ws_stats(ws, b);
+    if (table_override) { // value_transform path: the host supplies the table
+        for (int i = t; i < kBins; i += 1024) table[i] = table_override[(size_t)b * kBins + i];
+        return;
+    }
+    constexpr int kPer = kBins / 1024; // 64 bins per thread
+    unsigned long long local = 0;
+    unsigned int lmin = 0xffffffffu, lmax = 0;
+    for (int i = 0; i < kPer; ++i) {
+        const unsigned int c = hist[t * kPer + i];
+        local += c;
+        if (c) { lmin = min(lmin, (unsigned int)(t * kPer + i)); lmax = max(lmax, (unsigned int)(t * kPer + i)); }
+    }
+    s_part[t] = local;
+    if (t == 0) { s_mm[0] = 0xffffffffu; s_mm[1] = 0; }
+    __syncthreads();
+    if (lmin != 0xffffffffu) { atomicMin(&s_mm[0], lmin); atomicMax(&s_mm[1], lmax); }
+    // inclusive scan of 1024 partials (Hillis-Steele; 10 steps)
+    for (int o = 1; o < 1024; o <<= 1) {
+        unsigned long long add = (t >= o) ? s_part[t - o] : 0ull;
+        __syncthreads();
+        s_part[t] += add;
+        __syncthreads();
+    }
+    const unsigned long long n = s_part[1023];
+    const unsigned long long before = s_part[t] - local; // exclusive prefix of this thread's bins
+    if (n > 0) {
+        // wanted sorted positions: floor((n-1)*q) and +1 for both quantiles (and the medians)
+        double q[2] = {p_lo / 100.0, p_hi / 100.0};
+        if (mode == 2) { q[0] = 0.5; q[1] = 0.5; }
+        for (int k = 0; k < 2; ++k) {
+            const double virt = (double)(n - 1) * q[k];
+            const double prev = floor(virt);
+            unsigned long long i0 = (unsigned long long)prev, i1 = i0 + 1;
+            if (i1 > n - 1) i1 = n - 1;
+            // does this thread's bin range hold sorted element i0 / i1 ?
+            unsigned long long acc = before;
+            for (int i = 0; i < kPer; ++i) {
+                const unsigned int c = hist[t * kPer + i];
+                if (c) {
+                    if (i0 >= acc && i0 < acc + c) s_vals[2 * k] = (double)(t * kPer + i);
+                    if (i1 >= acc && i1 < acc + c) s_vals[2 * k + 1] = (double)(t * kPer + i);
+                }
+                acc += c;
+            }
+        }
+    }
+    __syncthreads();
+    if (t == 0) {
+        double vmin = 0.0, vmax = 0.0;
+        if (n > 0) {
+            if (mode == 2) {
+                // numpy median: mean of the two middle elements (they coincide for odd n)
+                const double virt = (double)(n - 1) * 0.5;
+                const bool odd = (n & 1ull) != 0;
+                (void)virt;
+                vmin = vmax = odd ? s_vals[0] : (s_vals[0] + s_vals[1]) / 2.0;
+            } else {
+                const double v0 = (double)(n - 1) * (p_lo / 100.0), v1 = (double)(n - 1) * (p_hi / 100.0);
+                vmin = numpy_lerp(s_vals[0], s_vals[1], v0 - floor(v0));
+                vmax = numpy_lerp(s_vals[2], s_vals[3], v1 - floor(v1));
+            }
+        }
+        if (mode == 1) { vmin = (double)s_mm[0]; vmax = (double)s_mm[1]; }
+        if (vmin_vmax_override) {
+            const double a = vmin_vmax_override[2 * b], c = vmin_vmax_override[2 * b + 1];
+            if (a == a) vmin = a;
+            if (c == c) vmax = c;
+        }
+        st->vmin = vmin; st->vmax = vmax; st->n_valid = n; st->vmin_u = s_mm[0]; st->vmax_u = s_mm[1];
+        if (vmin_vmax_out) { vmin_vmax_out[2 * b] = vmin; vmin_vmax_out[2 * b + 1] = vmax; }
+        if (median_out) median_out[b] = vmin;
+        s_vals[0] = vmin; s_vals[1] = vmax;
+    }
+    __syncthreads();
+    if (mode == 2) return;
+    const double vmin = s_vals[0], vmax = s_vals[1];
+    for (int i = t; i < kBins; i += 1024) {
+        unsigned int idx;
+        if (mode == 0) {
+            // colorize: x = (value - vmin)/(vmax - vmin) (f64), matplotlib: trunc(x*256) with
+            // x<0 -> under (row 0), x*256 == 256 -> 255, > 255 -> over (row 255)
+            double x = (vmin != vmax) ? ((double)i - vmin) / (vmax - vmin) : (double)i * 0.0;
+            x *= 256.0;
+            if (x < 0.0) idx = 0;
+            else if (x >= 256.0) idx = 255;
+            else idx = (unsigned int)x;
+        } else {
+            // np.uint8(255 * (d - min) / (max - min))
+            const double x = 255.0 * ((double)i - vmin) / (vmax - vmin);
+            idx = (x >= 0.0 && x < 256.0) ? (unsigned int)x : 0u; // values outside [min,max] never occur
+        }
+        table[i] = (uint8_t)idx;
+    }
+}
+
+// ---------------------------------------------------------------- K1 pass C: LUT application
+template <int OUT_CH> // 4: RGBA (colorize), 3: 3-byte colour (+ gray) for the min-max path
+__global__ void __launch_bounds__(256) apply_table_kernel(const uint16_t *__restrict__ u16, int64_t n_per_image, const uint8_t *__restrict__ lut,
+                                                          int has_invalid, unsigned int invalid_val, uint32_t bg, uint8_t *__restrict__ out,
+                                                          uint8_t *__restrict__ gray, void *ws) {
+    __shared__ uint32_t s_lut[256];
+    const int b = blockIdx.y;
+    if (lut) {
+        if (OUT_CH == 4) s_lut[threadIdx.x] = reinterpret_cast<const uint32_t *>(lut)[threadIdx.x];
+        else s_lut[threadIdx.x] = lut[3 * threadIdx.x] | (lut[3 * threadIdx.x + 1] << 8) | (lut[3 * threadIdx.x + 2] << 16);
+    }
+    __syncthreads();
+    const uint8_t *table = ws_table(ws, b);
+    const int64_t img_off = (int64_t)b * n_per_image;
+    for (int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; p < n_per_image; p += (int64_t)gridDim.x * blockDim.x * 4) {
+        unsigned int v[4];
+        const bool vec = (p + 3 < n_per_image) && (((img_off + p) & 3) == 0);
+        if (vec) {
+            const ushort4 d = *reinterpret_cast<const ushort4 *>(u16 + img_off + p);
+            v[0] = d.x; v[1] = d.y; v[2] = d.z; v[3] = d.w;
+        } else {
+            for (int j = 0; j < 4; ++j) v[j] = (p + j < n_per_image) ? u16[img_off + p + j] : 0u;
+        }
+        uint32_t c[4]; uint8_t g[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            g[j] = __ldg(table + v[j]);
+            c[j] = (has_invalid && v[j] == invalid_val) ? bg : s_lut[g[j]];
+        }
+        if (OUT_CH == 4) {
+            if (vec) {
+                *reinterpret_cast<uint4 *>(out + (img_off + p) * 4) = make_uint4(c[0], c[1], c[2], c[3]);
+            } else {
+                for (int j = 0; j < 4 && p + j < n_per_image; ++j) reinterpret_cast<uint32_t *>(out)[img_off + p + j] = c[j];
+            }
+        } else {
+            for (int j = 0; j < 4 && p + j < n_per_image; ++j) {
+                if (gray) gray[img_off + p + j] = g[j];
+                if (out) {
+                    uint8_t *o = out + (img_off + p + j) * 3;
+                    o[0] = c[j] & 0xff; o[1] = (c[j] >> 8) & 0xff; o[2] = (c[j] >> 16) & 0xff;
+                }
+            }
+        }
+    }
+}
+
+__global__ void scale_u16_kernel(const float *__restrict__ in, int64_t n, float scale_mul, uint16_t *__restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+    for (int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; p < n; p += stride) {
+        if (p + 3 < n) {
+            const float4 d = *reinterpret_cast<const float4 *>(in + p);
+            *reinterpret_cast<ushort4 *>(out + p) = make_ushort4((unsigned short)to_u16_sat(d.x, scale_mul), (unsigned short)to_u16_sat(d.y, scale_mul),
+                                                                 (unsigned short)to_u16_sat(d.z, scale_mul), (unsigned short)to_u16_sat(d.w, scale_mul));
+        } else {
+            for (int j = 0; p + j < n; ++j) out[p + j] = (unsigned short)to_u16_sat(in[p + j], scale_mul);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- a4: u16 -> metres
+__device__ __forceinline__ float depth_cvt(unsigned int u, float scale, float trunc) {
+    float p = (float)u / scale; // IEEE division, like Open3D's `*p /= (float)depth_scale`
+    if (trunc > 0.0f && p >= trunc) p = 0.0f;
+    return p;
+}
+__global__ void depth_from_u16_kernel(const uint16_t *__restrict__ in, int64_t n, float scale, float trunc, float *__restrict__ out) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x * 4;
+    for (int64_t p = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 4; p < n; p += stride) {
+        if (p + 3 < n) {
+            const ushort4 d = *reinterpret_cast<const ushort4 *>(in + p);
+            *reinterpret_cast<float4 *>(out + p) = make_float4(depth_cvt(d.x, scale, trunc), depth_cvt(d.y, scale, trunc),
+                                                               depth_cvt(d.z, scale, trunc), depth_cvt(d.w, scale, trunc));
+        } else {
+            for (int j = 0; p + j < n; ++j) out[p + j] = depth_cvt(in[p + j], scale, trunc);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- K2: back-projection + SE(3)
+constexpr int kBpMaxImages = 64;   // poses per launch, passed by value -> constant bank
+constexpr int kBpThreads = 256;
+constexpr int kBpPerThread = 4;
+constexpr int kBpPerBlock = kBpThreads * kBpPerThread;
+
+struct BackprojP {
+    float fx, fy, cx, cy;
+    int H, W, Hs, Ws, stride;
+    int blocks_per_image;
+    float pose[kBpMaxImages][12];
+};
+
+__device__ __forceinline__ float3 backproject_px(const BackprojP &bp, int img, int u, int v, float d) {
+    // pixel_to_3d (scaling_system.py:72-77): x = (u - cx) * depth / fx ; then the rigid transform
+    const float x = ((float)u - bp.cx) * d / bp.fx;
+    const float y = ((float)v - bp.cy) * d / bp.fy;
+    const float *M = bp.pose[img];
+    float3 p;
+    p.x = fmaf(M[0], x, fmaf(M[1], y, fmaf(M[2], d, M[3])));
+    p.y = fmaf(M[4], x, fmaf(M[5], y, fmaf(M[6], d, M[7])));
+    p.z = fmaf(M[8], x, fmaf(M[9], y, fmaf(M[10], d, M[11])));
+    return p;
+}
+
+// PHASE 0: per-block valid counts; PHASE 1: emit (offsets = exclusive scan of the counts)
+template <int PHASE>
+__global__ void __launch_bounds__(kBpThreads) backproject_kernel(const __grid_constant__ BackprojP bp, const float *__restrict__ depth,
+                                                                  const uint8_t *__restrict__ rgb_u8, int img0, int valid_only,
+                                                                  float *__restrict__ xyz, float *__restrict__ rgb, int64_t capacity,
+                                                                  long long *__restrict__ block_counts, const long long *__restrict__ block_offsets) {
+    __shared__ int s_warp[kBpThreads / 32];
+    const int img = blockIdx.y;
+    const int64_t n_vis = (int64_t)bp.Hs * bp.Ws;
+    const int64_t first = (int64_t)blockIdx.x * kBpPerBlock + threadIdx.x * kBpPerThread;
+    const float *dimg = depth + (int64_t)(img0 + img) * bp.H * bp.W;
+    float d[kBpPerThread]; int uu[kBpPerThread], vv[kBpPerThread];
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < kBpPerThread; ++j) {
+        const int64_t q = first + j;
+        d[j] = -1.0f;
+        if (q < n_vis) {
+            const int r = (int)(q / bp.Ws), c = (int)(q % bp.Ws);
+            vv[j] = r * bp.stride; uu[j] = c * bp.stride;
+            d[j] = __ldg(dimg + (int64_t)vv[j] * bp.W + uu[j]);
+            if (!(d[j] > 0.0f)) d[j] = 0.0f; // invalid but visited
+            cnt += (d[j] > 0.0f) || !valid_only;
+        }
+    }
+    // block exclusive scan of cnt
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    int inc = cnt;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+    int wbase = 0, total = 0;
+    for (int w = 0; w < kBpThreads / 32; ++w) {
+        if (w < wid) wbase += s_warp[w];
+        total += s_warp[w];
+    }
+    const int64_t gblock = (int64_t)img * bp.blocks_per_image + blockIdx.x;
+    if (PHASE == 0) {
+        if (threadIdx.x == 0) block_counts[gblock] = total;
+        return;
+    }
+    int64_t o = block_offsets[gblock] + wbase + inc - cnt;
+#pragma unroll
+    for (int j = 0; j < kBpPerThread; ++j) {
+        if (d[j] < 0.0f) continue;
+        const bool valid = d[j] > 0.0f;
+        if (!valid && valid_only) continue;
+        if (o < capacity) {
+            float3 p = make_float3(NAN, NAN, NAN);
+            if (valid) p = backproject_px(bp, img, uu[j], vv[j], d[j]);
+            xyz[3 * o + 0] = p.x; xyz[3 * o + 1] = p.y; xyz[3 * o + 2] = p.z;
+            if (rgb && rgb_u8) {
+                const uint8_t *c = rgb_u8 + ((int64_t)(img0 + img) * bp.H * bp.W + (int64_t)vv[j] * bp.W + uu[j]) * 3;
+                rgb[3 * o + 0] = valid ? c[0] / 255.0f : NAN;
+                rgb[3 * o + 1] = valid ? c[1] / 255.0f : NAN;
+                rgb[3 * o + 2] = valid ? c[2] / 255.0f : NAN;
+            }
+        }
+        ++o;
+    }
+}
+
+// exclusive scan of `n` block counts with a carried-in base; also writes per-image totals
+__global__ void __launch_bounds__(1024) scan_counts_kernel(const long long *counts, long long *offsets, int64_t n, int blocks_per_image,
+                                                           int n_images, long long *image_counts /*[n_images]*/, long long *running_total /*[1]*/) {
+    __shared__ long long s[1024];
+    __shared__ long long s_carry;
+    if (threadIdx.x == 0) s_carry = *running_total;
+    __syncthreads();
+    for (int64_t base = 0; base < n; base += 1024) {
+        const int64_t i = base + threadIdx.x;
+        const long long c = (i < n) ? counts[i] : 0;
+        s[threadIdx.x] = c;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            const long long add = (threadIdx.x >= o) ? s[threadIdx.x - o] : 0;
+            __syncthreads();
+            s[threadIdx.x] += add;
+            __syncthreads();
+        }
+        if (i < n) offsets[i] = s_carry + s[threadIdx.x] - c;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry += s[1023];
+        __syncthreads();
+    }
+    // per-image totals from the offsets (image k spans blocks [k*bpi, (k+1)*bpi))
+    for (int k = threadIdx.x; k < n_images; k += 1024) {
+        const long long lo = offsets[(int64_t)k * blocks_per_image];
+        const long long hi = (k + 1 < n_images) ? offsets[(int64_t)(k + 1) * blocks_per_image] : s_carry;
+        image_counts[k] = hi - lo;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *running_total = s_carry;
+}
+
+static int grid_for(int64_t work_items, int per_block) {
+    int64_t g = (work_items + per_block - 1) / per_block;
+    const int64_t cap = (int64_t)kNumSMs * 16;
+    if (g > cap) g = cap;
+    if (g < 1) g = 1;
+    return (int)g;
+}
+
+} // namespace bslam
+
+using namespace bslam;
+
+extern "C" {
+
+int bslam_scale_u16(const float *d_depth, int64_t n, float scale_mul, uint16_t *d_out, bslam_stream_t stream) {
+    BSLAM_CHECK_ARG(d_depth && d_out && n >= 0, "bslam_scale_u16: bad argument");
+    BSLAM_CHECK_ARG(((uintptr_t)d_depth & 15) == 0 && ((uintptr_t)d_out & 7) == 0, "bslam_scale_u16: buffers must be 16-byte aligned");
+    if (n == 0) return BSLAM_OK;
+    scale_u16_kernel<<<grid_for(n, 1024), 256, 0, (cudaStream_t)stream>>>(d_depth, n, scale_mul, d_out);
+    BSLAM_LAUNCH_CHECK();
+    return BSLAM_OK;
+}
+
+size_t bslam_colorize_workspace_bytes(int B) { return B > 0 ? (size_t)B * kWsPerImage + (size_t)B * 16 : 0; }
+
+static int run_hist(const float *d_depth_m, const uint16_t *d_u16_in, int B, int64_t n, float scale_mul, uint16_t *d_u16_out,
+                    int has_invalid, uint16_t invalid_val, void *ws, cudaStream_t st) {
+    BSLAM_CUDA(cudaMemsetAsync(ws, 0, bslam_colorize_workspace_bytes(B), st));
+    const dim3 grid((unsigned)((n + kPxPerBlock - 1) / kPxPerBlock), (unsigned)B);
+    if (d_depth_m) scale_hist_kernel<true><<<grid, kHistThreads, 0, st>>>(d_depth_m, nullptr, d_u16_out, n, scale_mul, has_invalid, invalid_val, ws);
+    else scale_hist_kernel<false><<<grid, kHistThreads, 0, st>>>(nullptr, d_u16_in, nullptr, n, scale_mul, has_invalid, invalid_val, ws);
+    BSLAM_LAUNCH_CHECK();
+    return BSLAM_OK;
+}
+
+int bslam_colorize(const float *d_depth_m, const uint16_t *d_u16_in, int B, int H, int W, float scale_mul, uint16_t *d_u16_out,
+                   uint8_t *d_rgba, const uint8_t *d_lut, double p_lo, double p_hi, int has_invalid, uint16_t invalid_val,
+                   uint32_t bg_rgba, const double *h_vmin_vmax, double *d_vmin_vmax_out, const uint8_t *d_table_override,
+                   void *d_workspace, bslam_stream_t stream) {
+    BSLAM_CHECK_ARG((d_depth_m != nullptr) != (d_u16_in != nullptr), "bslam_colorize: give exactly one of d_depth_m / d_u16_in");
+    BSLAM_CHECK_ARG(B > 0 && H > 0 && W > 0 && B <= 65535, "bslam_colorize: bad shape B=%d H=%d W=%d", B, H, W);
+    BSLAM_CHECK_ARG(d_rgba && d_lut && d_workspace, "bslam_colorize: NULL output / lut / workspace");
+    BSLAM_CHECK_ARG(!(d_depth_m && !d_u16_out), "bslam_colorize: float input needs d_u16_out (the metric-scaled image)");
+    BSLAM_CHECK_ARG(p_lo >= 0 && p_lo <= 100 && p_hi >= 0 && p_hi <= 100, "bslam_colorize: percentiles must be in [0,100]");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = (int64_t)H * W;
+    int rc = run_hist(d_depth_m, d_u16_in, B, n, scale_mul, d_u16_out, has_invalid, invalid_val, d_workspace, st);
+    if (rc) return rc;
+    double *d_override = nullptr;
+    if (h_vmin_vmax) {
+        d_override = (double *)((char *)d_workspace + (size_t)B * kWsPerImage);
+        BSLAM_CUDA(cudaMemcpyAsync(d_override, h_vmin_vmax, (size_t)B * 16, cudaMemcpyHostToDevice, st));
+    }
+    stats_table_kernel<<<B, 1024, 0, st>>>(d_workspace, p_lo, p_hi, d_override, d_vmin_vmax_out, nullptr, 0, d_table_override);
+    BSLAM_LAUNCH_CHECK();
+    const uint16_t *src = d_depth_m ? d_u16_out : d_u16_in;
+    const dim3 grid((unsigned)grid_for(n, 1024 * 4), (unsigned)B);
+    apply_table_kernel<4><<<grid, 256, 0, st>>>(src, n, d_lut, has_invalid, invalid_val, bg_rgba, d_rgba, nullptr, d_workspace);
+    BSLAM_LAUNCH_CHECK();
+    return BSLAM_OK;
+}
+
+int bslam_minmax_u8(const uint16_t *d_u16, int B, int H, int W, uint8_t *d_gray, uint8_t *d_rgb, const uint8_t *d_lut3,
+                    void *d_workspace, bslam_stream_t stream) {
+    BSLAM_CHECK_ARG(d_u16 && d_workspace && B > 0 && H > 0 && W > 0 && B <= 65535, "bslam_minmax_u8: bad argument");
+    BSLAM_CHECK_ARG(d_gray || d_rgb, "bslam_minmax_u8: no output requested");
+    BSLAM_CHECK_ARG(!(d_rgb && !d_lut3), "bslam_minmax_u8: colour output needs a 256x3 LUT");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = (int64_t)H * W;
+    int rc = run_hist(nullptr, d_u16, B, n, 1.0f, nullptr, 0, 0, d_workspace, st);
+    if (rc) return rc;
+    stats_table_kernel<<<B, 1024, 0, st>>>(d_workspace, 0, 100, nullptr, nullptr, nullptr, 1, nullptr);
+    BSLAM_LAUNCH_CHECK();
+    const dim3 grid((unsigned)grid_for(n, 1024 * 4), (unsigned)B);
+    apply_table_kernel<3><<<grid, 256, 0, st>>>(d_u16, n, d_lut3, 0, 0, 0, d_rgb, d_gray, d_workspace);
+    BSLAM_LAUNCH_CHECK();
+    return BSLAM_OK;
+}
+
+int bslam_median_u16(const uint16_t *d_u16, int B, int64_t n_per_image, int has_invalid, uint16_t invalid_val, double *d_out,
+                     void *d_workspace, bslam_stream_t stream) {
+    BSLAM_CHECK_ARG(d_u16 && d_out && d_workspace && B > 0 && B <= 65535 && n_per_image > 0, "bslam_median_u16: bad argument");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc = run_hist(nullptr, d_u16, B, n_per_image, 1.0f, nullptr, has_invalid, invalid_val, d_workspace, st);
+    if (rc) return rc;
+    stats_table_kernel<<<B, 1024, 0, st>>>(d_workspace, 50, 50, nullptr, nullptr, d_out, 2, nullptr);
+    BSLAM_LAUNCH_CHECK();
+    return BSLAM_OK;
+}
+
+int bslam_depth_from_u16(const uint16_t *d_in, int64_t n, float depth_scale, float depth_trunc, float *d_out, bslam_stream_t stream) {
+    BSLAM_CHECK_ARG(d_in && d_out && n >= 0 && depth_scale > 0, "bslam_depth_from_u16: bad argument");
+    BSLAM_CHECK_ARG(((uintptr_t)d_in & 7) == 0 && ((uintptr_t)d_out & 15) == 0, "bslam_depth_from_u16: buffers must be 16-byte aligned");
+    if (n == 0) return BSLAM_OK;
+    depth_from_u16_kernel<<<grid_for(n, 1024), 256, 0, (cudaStream_t)stream>>>(d_in, n, depth_scale, depth_trunc, d_out);
+    BSLAM_LAUNCH_CHECK();
+    return BSLAM_OK;
+}
+
+static int bp_blocks_per_image(int H, int W, int stride) {
+    const int64_t n_vis = (int64_t)((H + stride - 1) / stride) * ((W + stride - 1) / stride);
+    return (int)((n_vis + kBpPerBlock - 1) / kBpPerBlock);
+}
+
+size_t bslam_backproject_workspace_bytes(int B, int H, int W, int stride) {
+    if (B <= 0 || H <= 0 || W <= 0 || stride <= 0) return 0;
+    return (size_t)B * bp_blocks_per_image(H, W, stride) * 16 + 256;
+}
+
+int bslam_backproject(const float *d_depth, const uint8_t *d_rgb_u8, int B, int H, int W, int stride, const float *h_K,
+                      const float *h_cam_to_world, int valid_only, float *d_xyz, float *d_rgb, int64_t capacity,
+                      int64_t *d_counts, void *d_workspace, bslam_stream_t stream) {
+    BSLAM_CHECK_ARG(d_depth && h_K && h_cam_to_world && d_xyz && d_counts && d_workspace, "bslam_backproject: NULL argument");
+    BSLAM_CHECK_ARG(B > 0 && H > 0 && W > 0 && stride > 0, "bslam_backproject: bad shape");
+    BSLAM_CHECK_ARG(!(d_rgb && !d_rgb_u8), "bslam_backproject: colour output needs the RGB8 image");
+    cudaStream_t st = (cudaStream_t)stream;
+    static thread_local BackprojP bp;
+    bp.fx = h_K[0]; bp.fy = h_K[1]; bp.cx = h_K[2]; bp.cy = h_K[3];
+    bp.H = H; bp.W = W; bp.stride = stride;
+    bp.Hs = (H + stride - 1) / stride; bp.Ws = (W + stride - 1) / stride;
+    bp.blocks_per_image = bp_blocks_per_image(H, W, stride);
+    long long *counts = (long long *)((char *)d_workspace + 256);
+    long long *offsets = counts + (size_t)B * bp.blocks_per_image;
+    long long *running = (long long *)d_workspace;
+    BSLAM_CUDA(cudaMemsetAsync(running, 0, 8, st));
+    for (int i0 = 0; i0 < B; i0 += kBpMaxImages) {
+        const int nb = (B - i0 < kBpMaxImages) ? B - i0 : kBpMaxImages;
+        memcpy(bp.pose, h_cam_to_world + (size_t)i0 * 12, (size_t)nb * 12 * sizeof(float));
+        const dim3 grid((unsigned)bp.blocks_per_image, (unsigned)nb);
+        long long *c = counts + (size_t)i0 * bp.blocks_per_image, *o = offsets + (size_t)i0 * bp.blocks_per_image;
+        backproject_kernel<0><<<grid, kBpThreads, 0, st>>>(bp, d_depth, d_rgb_u8, i0, valid_only, d_xyz, d_rgb, capacity, c, o);
+        BSLAM_LAUNCH_CHECK();
+        scan_counts_kernel<<<1, 1024, 0, st>>>(c, o, (int64_t)nb * bp.blocks_per_image, bp.blocks_per_image, nb,
+                                                (long long *)d_counts + i0, running);
+        BSLAM_LAUNCH_CHECK();
+        backproject_kernel<1><<<grid, kBpThreads, 0, st>>>(bp, d_depth, d_rgb_u8, i0, valid_only, d_xyz, d_rgb, capacity, c, o);
+        BSLAM_LAUNCH_CHECK();
+    }
+    BSLAM_CUDA(cudaMemcpyAsync((long long *)d_counts + B, running, 8, cudaMemcpyDeviceToDevice, st));
+    return BSLAM_OK;
+}
+
+} // extern "C"

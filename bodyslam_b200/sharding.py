@@ -1,0 +1,208 @@
+"""z-slab sharding of the TSDF volume over the GPUs of one box (one process per GPU).
+
+The reference has no multi-device code at all; this is the one parallel axis the
+hot path offers: every voxel depends only on (its coordinates, the frame, the pose), so the grid
+is cut into contiguous z-slabs, each rank integrates every frame into its own slab with NO
+data-path collective, and only surface extraction exchanges data:
+  * one halo plane each way between neighbouring slabs (send/recv), so cubes straddling a slab
+    boundary are emitted exactly once (by the lower slab) and their shared vertices exactly once
+    (by the slab owning the edge);
+  * a gather of the per-slab meshes to rank 0, where vertex ids are rebased and the references
+    into the next slab's first plane are resolved -- the result equals the single-GPU mesh after
+    canonical ordering.
+Frames reach the ranks either from each rank's own copy (synthetic / shared storage) or by a
+broadcast from rank 0 (`broadcast_frames`), which is the only NCCL traffic during integration.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .geometry import TriangleMesh
+
+BRICK = 8
+
+
+def slab_bounds(nz: int, world_size: int):
+    """contiguous [z0, z1) per rank; every boundary is a multiple of the brick edge (8)."""
+    nb = (nz + BRICK - 1) // BRICK
+    if world_size > nb:
+        raise ValueError(f"cannot cut {nz} planes into {world_size} slabs of whole bricks")
+    base, extra = divmod(nb, world_size)
+    out, b = [], 0
+    for r in range(world_size):
+        n = base + (1 if r < extra else 0)
+        out.append((b * BRICK, min((b + n) * BRICK, nz)))
+        b += n
+    return out
+
+
+def merge_slab_meshes(meshes, z_offsets, ny: int) -> TriangleMesh:
+    """Concatenate per-slab meshes (ordered bottom to top) into one mesh.
+
+    Vertex ids are rebased by the running vertex count; a negative id -(1 + (x*ny + y)*4 + axis)
+    refers to the vertex on edge (x, y, z=0, axis) of the NEXT slab and is resolved through that
+    slab's vertex keys.  Keys are returned with global z.  Works on torch tensors (any device).
+    """
+    import torch
+
+    n = len(meshes)
+    bases, acc = [], 0
+    for m in meshes:
+        bases.append(acc)
+        acc += int(m.vertices.shape[0])
+    verts, keys, cols, tris = [], [], [], []
+    for i, m in enumerate(meshes):
+        k = m.vertex_keys.clone()
+        k[:, 2] += int(z_offsets[i])
+        verts.append(m.vertices)
+        keys.append(k)
+        if m.vertex_colors is not None:
+            cols.append(m.vertex_colors)
+        t = m.triangles.to(torch.int64).clone()
+        neg = t < 0
+        if bool(neg.any()):
+            if i + 1 >= n:
+                raise RuntimeError("merge_slab_meshes: the top slab references a slab above it")
+            nk = meshes[i + 1].vertex_keys.to(torch.int64)
+            plane0 = torch.nonzero(nk[:, 2] == 0).reshape(-1)
+            code = (nk[plane0, 0] * ny + nk[plane0, 1]) * 4 + nk[plane0, 3]
+            order = torch.argsort(code)
+            code_sorted = code[order]
+            want = -t[neg] - 1
+            pos = torch.searchsorted(code_sorted, want)
+            pos = pos.clamp_max(max(code_sorted.numel() - 1, 0))
+            if code_sorted.numel() == 0 or not bool((code_sorted[pos] == want).all()):
+                raise RuntimeError("merge_slab_meshes: unresolved cross-slab vertex reference")
+            t[neg] = plane0[order[pos]] + bases[i + 1]
+        t[~neg] += bases[i]
+        tris.append(t.to(torch.int32))
+    cat = lambda xs, shape, dt: torch.cat(xs) if xs else torch.empty(shape, dtype=dt)
+    return TriangleMesh(torch.cat(verts), torch.cat(tris), torch.cat(cols) if len(cols) == n and n else None, torch.cat(keys))
+
+
+def broadcast_frames(depth, color, extrinsics, src: int = 0, group=None):
+    """Broadcast one batch of frames from `src` to every rank (NCCL over NVLink on the GPU box).
+
+    depth/color are pre-allocated tensors of identical shape on every rank; extrinsics a float64
+    tensor [F,4,4] on the same device.  Returns the tensors (filled in place)."""
+    import torch.distributed as dist
+
+    works = [dist.broadcast(depth, src, group=group, async_op=True)]
+    if color is not None:
+        works.append(dist.broadcast(color, src, group=group, async_op=True))
+    works.append(dist.broadcast(extrinsics, src, group=group, async_op=True))
+    for w in works:
+        w.wait()
+    return depth, color, extrinsics
+
+
+def exchange_halo_planes(top_plane, bottom_plane, rank: int, world_size: int, group=None):
+    """neighbour exchange: returns (halo_lo, halo_hi) = (top plane of rank-1, bottom plane of rank+1)."""
+    import torch
+    import torch.distributed as dist
+
+    halo_lo = torch.empty_like(top_plane) if rank > 0 else None
+    halo_hi = torch.empty_like(bottom_plane) if rank + 1 < world_size else None
+    ops_ = []
+    if rank + 1 < world_size:
+        ops_.append(dist.P2POp(dist.isend, top_plane, rank + 1, group))
+        ops_.append(dist.P2POp(dist.irecv, halo_hi, rank + 1, group))
+    if rank > 0:
+        ops_.append(dist.P2POp(dist.isend, bottom_plane, rank - 1, group))
+        ops_.append(dist.P2POp(dist.irecv, halo_lo, rank - 1, group))
+    if ops_:
+        for w in dist.batch_isend_irecv(ops_):
+            w.wait()
+    return halo_lo, halo_hi
+
+
+def gather_meshes(mesh: TriangleMesh, rank: int, world_size: int, dst: int = 0, group=None):
+    """variable-size gather of per-rank meshes to `dst` -> list of TriangleMesh (None elsewhere)."""
+    import torch
+    import torch.distributed as dist
+
+    dev = mesh.vertices.device
+    has_col = mesh.vertex_colors is not None
+    mine = torch.tensor([mesh.vertices.shape[0], mesh.triangles.shape[0], int(has_col)], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros_like(mine) for _ in range(world_size)]
+    dist.all_gather(sizes, mine, group=group)
+    sizes = [s.tolist() for s in sizes]
+    if rank != dst:
+        ops_ = [dist.P2POp(dist.isend, mesh.vertices.contiguous(), dst, group),
+                dist.P2POp(dist.isend, mesh.vertex_keys.contiguous(), dst, group),
+                dist.P2POp(dist.isend, mesh.triangles.contiguous(), dst, group)]
+        if has_col:
+            ops_.append(dist.P2POp(dist.isend, mesh.vertex_colors.contiguous(), dst, group))
+        ops_ = [o for o in ops_ if o.tensor.numel() > 0]
+        if ops_:
+            for w in dist.batch_isend_irecv(ops_):
+                w.wait()
+        return None
+    out, ops_ = [], []
+    for r in range(world_size):
+        if r == dst:
+            out.append(mesh)
+            continue
+        V, T, c = sizes[r]
+        m = TriangleMesh(torch.empty((V, 3), dtype=torch.float32, device=dev), torch.empty((T, 3), dtype=torch.int32, device=dev),
+                         torch.empty((V, 3), dtype=torch.float32, device=dev) if c else None,
+                         torch.empty((V, 4), dtype=torch.int32, device=dev))
+        for t in (m.vertices, m.vertex_keys, m.triangles, m.vertex_colors):
+            if t is not None and t.numel() > 0:
+                ops_.append(dist.P2POp(dist.irecv, t, r, group))
+        out.append(m)
+    if ops_:
+        for w in dist.batch_isend_irecv(ops_):
+            w.wait()
+    return out
+
+
+class ShardedTSDF:
+    """One z-slab of a dense TSDF per rank; same surface as `TSDF` for integration, mesh on rank 0.
+
+    Every rank calls every method (SPMD).  `integrate_batch` is collective-free; pass
+    `broadcast_from=0` when only rank 0 holds the frames.
+    """
+
+    def __init__(self, voxel_length=0.001, sdf_trunc=0.1, resolution=512, origin=None, color=True, device=None,
+                 rank=None, world_size=None, group=None):
+        import torch.distributed as dist
+
+        from .tsdf import DenseTSDFVolume
+
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world_size = dist.get_world_size(group) if world_size is None else world_size
+        if np.isscalar(resolution):
+            resolution = (int(resolution),) * 3
+        self.nx, self.ny, self.nz = resolution
+        self.bounds = slab_bounds(self.nz, self.world_size)
+        z0, z1 = self.bounds[self.rank]
+        if origin is None:
+            origin = tuple(-0.5 * n * voxel_length for n in resolution)
+        self.tsdf = DenseTSDFVolume(voxel_length, sdf_trunc, (self.nx, self.ny, z1 - z0), origin, color=color, device=device,
+                                    gz0=z0, z_total=self.nz)
+
+    def integrate_batch(self, depth, color, intrinsic, extrinsics, broadcast_from=None):
+        if broadcast_from is not None and self.world_size > 1:
+            import torch
+
+            E = torch.as_tensor(np.asarray(extrinsics, dtype=np.float64), device=depth.device).reshape(-1, 4, 4).contiguous()
+            broadcast_frames(depth, color, E, broadcast_from, self.group)
+            extrinsics = E.cpu().numpy()
+        self.tsdf.integrate_batch(depth, color, intrinsic, extrinsics)
+
+    def build_3D_map(self, rgbd, intrinsic, extrinsic):
+        self.tsdf.integrate(rgbd, intrinsic, extrinsic)
+
+    def extract_mesh(self):
+        """full mesh on rank 0 (None on the other ranks)"""
+        v = self.tsdf
+        if self.world_size == 1:
+            return v.extract_triangle_mesh()
+        lo, hi = exchange_halo_planes(v.export_plane(v.nz - 1), v.export_plane(0), self.rank, self.world_size, self.group)
+        mesh = v.extract_triangle_mesh(halo_lo=lo, halo_hi=hi)
+        parts = gather_meshes(mesh, self.rank, self.world_size, 0, self.group)
+        if parts is None:
+            return None
+        return merge_slab_meshes(parts, [b[0] for b in self.bounds], self.ny)

@@ -1,0 +1,268 @@
+"""3DM reconstruction entry points -- drop-in for the reference's `N/3DM/tsdf.py`.
+
+`TSDF` keeps the reference signatures (tsdf.py:5-52): `TSDF(voxel_length, sdf_trunc)`, `.tsdf`,
+`build_3D_map`, `build_copy_3D_map`, `extract_pcd`, `extract_mesh`, `save_pcd`, `save_mesh`.
+Where the reference wraps Open3D's CPU `ScalableTSDFVolume`, `.tsdf` here is a
+`DenseTSDFVolume`: the dense N^3 equivalent (Open3D UniformTSDFVolume semantics) living
+brick-ordered in B200 HBM and driven by the hand-written kernels in csrc/.  Extra, non-breaking
+keyword arguments choose the box (`resolution`, `origin`), colour integration and the device.
+"""
+from __future__ import annotations
+
+import copy as _copy
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib, ops
+from .geometry import PointCloud, TriangleMesh, intrinsic_params, to_numpy
+
+
+class DenseTSDFVolume:
+    """Dense TSDF box on one GPU.  Method names follow Open3D's volume (`integrate`,
+    `extract_triangle_mesh`, `extract_point_cloud`, `reset`) so reference code that reaches through
+    `TSDF.tsdf` keeps working.
+
+    resolution : int or (nx, ny, nz) voxels;  origin : world position of the grid corner
+    (default: the cube is centred on the world origin);  gz0 : global z index of local plane 0
+    (z-slab sharding, multiple of 8);  color : integrate RGB8 like the reference's
+    `TSDFVolumeColorType.RGB8` (tsdf.py:10).
+    """
+
+    def __init__(self, voxel_length: float, sdf_trunc: float, resolution=512, origin=None, color: bool = True,
+                 device=None, gz0: int = 0, z_total: int | None = None):
+        torch = _lib.require_cuda()
+        self._L = _lib.load()
+        self.device = ops._device(device)
+        if np.isscalar(resolution):
+            resolution = (int(resolution),) * 3
+        self.nx, self.ny, self.nz = (int(r) for r in resolution)
+        self.voxel_length = float(voxel_length)
+        self.sdf_trunc = float(sdf_trunc)
+        self.gz0 = int(gz0)
+        self.z_total = int(z_total) if z_total is not None else self.nz
+        if origin is None:
+            origin = (-0.5 * self.nx * self.voxel_length, -0.5 * self.ny * self.voxel_length, -0.5 * self.z_total * self.voxel_length)
+        self.origin = np.ascontiguousarray(origin, dtype=np.float64)
+        self.color = bool(color)
+        nbytes = self._L.bslam_tsdf_storage_bytes(self.nx, self.ny, self.nz, int(self.color))
+        self._storage = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self._h = C.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.bslam_tsdf_create(C.byref(self._h), self.nx, self.ny, self.nz, self.gz0, self.voxel_length,
+                                                 self.sdf_trunc, _lib.ptr(self.origin), int(self.color), self.device.index,
+                                                 _lib.ptr(self._storage), _lib.stream_ptr(self.device)))
+        self.frames_integrated = 0
+
+    # ------------------------------------------------------------------ lifetime
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            try:
+                self._L.bslam_tsdf_destroy(h)
+            except Exception:
+                pass
+            self._h = C.c_void_p()
+
+    def __deepcopy__(self, memo):
+        """`deepcopy(self.tsdf)` of tsdf.py:24 -> device-to-device clone."""
+        torch = _lib.require_cuda()
+        other = DenseTSDFVolume(self.voxel_length, self.sdf_trunc, (self.nx, self.ny, self.nz), self.origin, self.color,
+                                self.device, self.gz0, self.z_total)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.bslam_tsdf_copy(self._h, other._h, _lib.stream_ptr(self.device)))
+        other.frames_integrated = self.frames_integrated
+        return other
+
+    def reset(self):
+        torch = _lib.require_cuda()
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.bslam_tsdf_reset(self._h, _lib.stream_ptr(self.device)))
+        self.frames_integrated = 0
+
+    # ------------------------------------------------------------------ integration
+    def _check_frame(self, depth, color, intrinsic):
+        W, H, fx, fy, cx, cy = intrinsic_params(intrinsic)
+        if depth.dim() == 2:
+            depth = depth.unsqueeze(0)
+        if depth.dim() != 3 or depth.shape[1] != H or depth.shape[2] != W:
+            raise RuntimeError("[DenseTSDFVolume::Integrate] Unsupported image format.")
+        if self.color:
+            if color is None or color.numel() != depth.shape[0] * H * W * 3:
+                raise RuntimeError("[DenseTSDFVolume::Integrate] Unsupported image format.")
+        return depth, (W, H, fx, fy, cx, cy)
+
+    def integrate(self, rgbd, intrinsic, extrinsic, zmarch: int = _lib.ZMARCH_BRICK):
+        """Open3D `volume.integrate(rgbd, intrinsic, extrinsic)` -- one frame (tsdf.py:22).
+
+        rgbd: object with `.depth` (H,W f32 metres) and `.color` (H,W,3 u8); numpy, torch CPU/CUDA
+        or Open3D images.  extrinsic: 4x4 world->camera (f64).
+        """
+        torch = _lib.require_cuda()
+        name = ops._dtype_name(rgbd.depth)
+        if name != "float32":
+            raise RuntimeError("[DenseTSDFVolume::Integrate] Unsupported image format.")
+        depth = ops.as_cuda(rgbd.depth, torch.float32, self.device)
+        color = None
+        if self.color:
+            c = getattr(rgbd, "color", None)
+            if c is None or ops._dtype_name(c) != "uint8":
+                raise RuntimeError("[DenseTSDFVolume::Integrate] Unsupported image format.")
+            color = ops.as_cuda(c, torch.uint8, self.device)
+        self.integrate_batch(depth, color, intrinsic, np.asarray(to_numpy(extrinsic), dtype=np.float64).reshape(1, 4, 4), zmarch=zmarch)
+
+    def integrate_batch(self, depth, color, intrinsic, extrinsics, zmarch: int = _lib.ZMARCH_BRICK, update_counts=None, dry_run=False):
+        """F frames in order (the `update_map_after_pg` replay shape, slam_utils.py:124-135).
+
+        depth [F,H,W] f32 CUDA (or anything `as_cuda` takes), color [F,H,W,3] u8 or None,
+        extrinsics [F,4,4] f64 world->camera.  update_counts: optional u64-as-i64 CUDA tensor [F]
+        accumulating the number of voxels updated per frame.
+        """
+        torch = _lib.require_cuda()
+        depth = ops.as_cuda(depth, torch.float32, self.device)
+        if color is not None:
+            color = ops.as_cuda(color, torch.uint8, self.device)
+        depth, (W, H, fx, fy, cx, cy) = self._check_frame(depth, color if self.color else None, intrinsic)
+        F = depth.shape[0]
+        E = np.ascontiguousarray(np.asarray(to_numpy(extrinsics), dtype=np.float64).reshape(-1, 16))
+        if E.shape[0] != F:
+            raise RuntimeError(f"integrate_batch: {F} frames but {E.shape[0]} extrinsics")
+        K = np.array([fx, fy, cx, cy], dtype=np.float64)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.bslam_tsdf_integrate(self._h, _lib.ptr(depth), _lib.ptr(color) if self.color else None, F, H, W,
+                                                    _lib.ptr(K), _lib.ptr(E), int(zmarch), _lib.ptr(update_counts), int(bool(dry_run)),
+                                                    _lib.stream_ptr(self.device)))
+        if not dry_run:
+            self.frames_integrated += F
+
+    def count_updates(self, depth, intrinsic, extrinsics, zmarch: int = _lib.ZMARCH_BRICK):
+        """U_f of SURVEY.md 8(d): voxels each frame WOULD update (volume untouched) -> i64 [F]."""
+        torch = _lib.require_cuda()
+        depth = ops.as_cuda(depth, torch.float32, self.device)
+        F = 1 if depth.dim() == 2 else depth.shape[0]
+        counts = torch.zeros(F, dtype=torch.int64, device=self.device)
+        col, self.color = self.color, False
+        try:
+            self.integrate_batch(depth, None, intrinsic, extrinsics, zmarch=zmarch, update_counts=counts, dry_run=True)
+        finally:
+            self.color = col
+        return counts
+
+    def profile(self, enable: bool = True):
+        """bracket the dominant integrate kernel with CUDA events (bench.py roofline)"""
+        _lib.check(self._L.bslam_tsdf_profile(self._h, int(bool(enable))))
+
+    def profile_read(self):
+        """-> (accumulated kernel ms, launches) since profile(True); synchronises"""
+        ms, n = C.c_double(), C.c_longlong()
+        _lib.check(self._L.bslam_tsdf_profile_read(self._h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    # ------------------------------------------------------------------ dense views (parity / interchange)
+    def export_dense(self, with_color: bool = False):
+        """(tsdf, weight[, color]) as [nx,ny,nz] f32 CUDA tensors in Open3D order x*ny*nz + y*nz + z."""
+        torch = _lib.require_cuda()
+        n = self.nx * self.ny * self.nz
+        t = torch.empty(n, dtype=torch.float32, device=self.device)
+        w = torch.empty(n, dtype=torch.float32, device=self.device)
+        c = torch.empty(n * 3, dtype=torch.float32, device=self.device) if (with_color and self.color) else None
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.bslam_tsdf_export(self._h, _lib.ptr(t), _lib.ptr(w), _lib.ptr(c), _lib.stream_ptr(self.device)))
+        shp = (self.nx, self.ny, self.nz)
+        out = (t.view(shp), w.view(shp))
+        return out + (c.view(shp + (3,)),) if c is not None else out
+
+    def import_dense(self, tsdf, weight, color=None):
+        torch = _lib.require_cuda()
+        t = ops.as_cuda(tsdf, torch.float32, self.device)
+        w = ops.as_cuda(weight, torch.float32, self.device)
+        c = ops.as_cuda(color, torch.float32, self.device) if (color is not None and self.color) else None
+        if t.numel() != self.nx * self.ny * self.nz or w.numel() != t.numel():
+            raise RuntimeError("import_dense: shape mismatch")
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.bslam_tsdf_import(self._h, _lib.ptr(t), _lib.ptr(w), _lib.ptr(c), _lib.stream_ptr(self.device)))
+
+    def export_plane(self, z: int):
+        """{tsdf, weight} of local plane z as a [nx, ny, 2] f32 CUDA tensor (slab halo)."""
+        torch = _lib.require_cuda()
+        p = torch.empty((self.nx, self.ny, 2), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.bslam_tsdf_export_plane(self._h, int(z), _lib.ptr(p), _lib.stream_ptr(self.device)))
+        return p
+
+    # ------------------------------------------------------------------ extraction
+    def extract_triangle_mesh(self, halo_lo=None, halo_hi=None) -> TriangleMesh:
+        """Open3D `extract_triangle_mesh()` (tsdf.py:43) -- compacted marching cubes on the GPU."""
+        torch = _lib.require_cuda()
+        cnt = np.zeros(2, np.int64)
+        with torch.cuda.device(self.device):
+            st = _lib.stream_ptr(self.device)
+            _lib.check(self._L.bslam_mc_count(self._h, _lib.ptr(halo_lo), _lib.ptr(halo_hi), _lib.ptr(cnt), st))
+            V, T = int(cnt[0]), int(cnt[1])
+            verts = torch.empty((V, 3), dtype=torch.float32, device=self.device)
+            keys = torch.empty((V, 4), dtype=torch.int32, device=self.device)
+            cols = torch.empty((V, 3), dtype=torch.float32, device=self.device) if self.color else None
+            tris = torch.empty((T, 3), dtype=torch.int32, device=self.device)
+            if V or T:
+                _lib.check(self._L.bslam_mc_emit(self._h, _lib.ptr(halo_lo), _lib.ptr(halo_hi), _lib.ptr(verts), _lib.ptr(keys),
+                                                 _lib.ptr(cols), V, _lib.ptr(tris), T, st))
+        return TriangleMesh(verts, tris, cols, keys)
+
+    def extract_point_cloud(self, normals: bool = True) -> PointCloud:
+        """Open3D `extract_point_cloud()` (tsdf.py:40)."""
+        torch = _lib.require_cuda()
+        cnt = np.zeros(1, np.int64)
+        with torch.cuda.device(self.device):
+            st = _lib.stream_ptr(self.device)
+            _lib.check(self._L.bslam_points_count(self._h, _lib.ptr(cnt), st))
+            P = int(cnt[0])
+            pts = torch.empty((P, 3), dtype=torch.float32, device=self.device)
+            nrm = torch.empty((P, 3), dtype=torch.float32, device=self.device) if normals else None
+            cols = torch.empty((P, 3), dtype=torch.float32, device=self.device) if self.color else None
+            keys = torch.empty((P, 4), dtype=torch.int32, device=self.device)
+            if P:
+                _lib.check(self._L.bslam_points_emit(self._h, _lib.ptr(pts), _lib.ptr(nrm), _lib.ptr(cols), _lib.ptr(keys), P, st))
+        return PointCloud(pts, cols, nrm, keys)
+
+
+class TSDF:
+    """Drop-in for the reference's `TSDF` (N/3DM/tsdf.py:5-52)."""
+
+    def __init__(self, voxel_length: float = 0.001, sdf_trunc: float = 0.1, resolution=512, origin=None,
+                 color: bool = True, device=None):
+        self.tsdf = DenseTSDFVolume(voxel_length=voxel_length, sdf_trunc=sdf_trunc, resolution=resolution, origin=origin,
+                                    color=color, device=device)
+
+    def build_3D_map(self, rgbd, intrinsic, extrinsic):
+        '''
+        This function reconstruct the 3D model from the pseudo-rgbd using TSDF
+        :param rgbd: pseudo-rgbd
+        :param intrinsic: intrinsic parameter of the camera
+        :param extrinsic: the global position of the camera
+        :return:
+        '''
+        self.tsdf.integrate(rgbd, intrinsic, extrinsic)
+
+    def build_copy_3D_map(self, rgbd, intrinsic, extrinsic):
+        tsdf_copy = _copy.deepcopy(self.tsdf)
+        tsdf_copy.integrate(rgbd, intrinsic, extrinsic)
+        return tsdf_copy
+
+    def save_pcd(self, saving_path: str):
+        from .io import write_point_cloud
+
+        pcd = self.tsdf.extract_point_cloud()
+        write_point_cloud(saving_path, pcd)
+
+    def extract_pcd(self):
+        return self.tsdf.extract_point_cloud()
+
+    def extract_mesh(self) -> TriangleMesh:
+        return self.tsdf.extract_triangle_mesh()
+
+    def save_mesh(self, saving_path: str):
+        from .io import write_triangle_mesh
+
+        mesh = self.extract_mesh()
+        write_triangle_mesh(saving_path, mesh)
