@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--resolution", type=int, default=0, help="override the 512^3 grid (debug only; invalidates the metric)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mc", action="store_true")
+    ap.add_argument("--batch", type=int, default=0, help="frames per integrate launch (0 = library default)")
     ap.add_argument("--color", action="store_true", help="also integrate RGB8 colour (reported as an extra, not the headline)")
     return ap.parse_args()
 
@@ -207,6 +208,8 @@ def main():
     E_dev = torch.as_tensor(E, device=dev).contiguous()
     z0, z1 = slab_bounds(res, world)[rank]
     vol = DenseTSDFVolume(vl, trunc, (res, res, z1 - z0), cfg["origin"], color=False, device=dev, gz0=z0, z_total=res)
+    if args.batch:
+        vol.set_batch(args.batch)
     depth_f = torch.empty((F, H, W), dtype=torch.float32, device=dev)
     L = _lib.load()
 
@@ -261,6 +264,9 @@ def main():
     k_ms, k_launches = vol.profile_read()
     vol.profile(False)
     fps = args.steps * F / (ms_total / 1e3)
+    if rank == 0:
+        print(f"[bench] resident: {fps:.1f} frames/s, {ms_total / args.steps:.2f} ms/step, integrate kernel {k_ms / max(k_launches, 1):.3f} ms x "
+              f"{k_launches} launches, U_f mean {uf_total / F:.0f} voxels/frame", file=sys.stderr)
 
     # ---- end to end: pinned host buffers -> H2D -> a4 -> K3 -> D2H of the per-frame update counts
     host_u16 = torch.empty((F, H, W), dtype=torch.uint16).pin_memory() if rank == 0 else None
@@ -286,6 +292,8 @@ def main():
     barrier()
     ms_e2e = max_over_ranks(ev0.elapsed_time(ev1))
     fps_e2e = args.steps * F / (ms_e2e / 1e3)
+    if rank == 0:
+        print(f"[bench] e2e: {fps_e2e:.1f} frames/s, {ms_e2e / args.steps:.2f} ms/step", file=sys.stderr)
 
     # ---- one surface extraction (config 4: "integrate all frames then one marching cubes")
     extras = {}
@@ -314,7 +322,7 @@ def main():
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ids = np.linspace(0, F - 1, 24).astype(int)
-        sample_np = depth_u16[torch.as_tensor(ids, device=dev)].cpu().numpy()
+        sample_np = depth_u16.view(torch.int16)[torch.as_tensor(ids, device=dev)].view(torch.uint16).cpu().numpy()
         cpu_fps, n_cpu, cpu_counts, cores = cpu_sample(cfg, E, sample_np, ids, res, vl, trunc)
         gpu_counts = uf.cpu().numpy()[ids[:n_cpu]].tolist()
         cpu = {"value": cpu_fps, "unit": UNIT, "cores": cores, "kind": "port",
@@ -324,7 +332,7 @@ def main():
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        launches_per_step = 1 + 3 * ((F + 255) // 256)
+        launches_per_step = 1 + 3 * ((F + (args.batch or 256) - 1) // (args.batch or 256))
         ach = (bytes_algo_local * args.steps / 1e9) / (k_ms / 1e3) if k_ms > 0 else None
         line = {
             "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

@@ -76,6 +76,7 @@ struct bslam_volume {
     void *int_scratch;
     size_t int_scratch_bytes;
     // optional per-launch timing of the dominant kernel (bslam_tsdf_profile)
+    int batch; // frames per integrate launch (0 = default)
     int prof_enabled, prof_n;
     cudaEvent_t prof_ev[2 * 64];
     double prof_ms_accum;

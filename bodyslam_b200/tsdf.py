@@ -149,6 +149,10 @@ class DenseTSDFVolume:
             self.color = col
         return counts
 
+    def set_batch(self, frames_per_launch: int):
+        """frames per integrate launch (0 = library default, max 256)"""
+        _lib.check(self._L.bslam_tsdf_set_batch(self._h, int(frames_per_launch)))
+
     def profile(self, enable: bool = True):
         """bracket the dominant integrate kernel with CUDA events (bench.py roofline)"""
         _lib.check(self._L.bslam_tsdf_profile(self._h, int(bool(enable))))

@@ -160,6 +160,16 @@ BSLAM_API int bslam_tsdf_integrate(bslam_volume *vol, const float *d_depth, cons
                                    unsigned long long *d_update_counts, int dry_run,
                                    bslam_stream_t stream);
 
+/* frames per integrate launch (1..BSLAM_MAX_BATCH, 0 = library default).  Larger batches keep a
+ * voxel in registers across more frames; smaller ones keep the batch's depth images L2-resident. */
+BSLAM_API int bslam_tsdf_set_batch(bslam_volume *vol, int frames_per_launch);
+
+/* Device self-test: n random operand triples through the kernels' shared-reciprocal division and
+ * magic-number floor, compared with IEEE `/` and (int) casts; returns the number of mismatches
+ * (must be 0).  Synchronises the stream. */
+BSLAM_API int bslam_selftest(unsigned long long n, unsigned int seed, unsigned long long *h_mismatches,
+                             bslam_stream_t stream);
+
 /* Measurement hook (bench.py roofline): when enabled, the dominant kernel of every integrate
  * launch (brick_integrate_kernel) is bracketed by CUDA events on the launch stream.  Up to 64
  * launches are buffered between reads; bslam_tsdf_profile_read synchronises on them and returns

@@ -182,3 +182,26 @@ def test_tsdf_dropin_api_and_errors(cuda):
     z = RGBDImage(sc["color"][0], np.zeros((sc["H"], sc["W"]), np.float32))
     tsdf.build_3D_map(z, sc["intrinsic"], sc["E"][0])
     assert torch.equal(tsdf.tsdf.export_dense()[1], w0)
+
+
+def test_device_arithmetic_selftest(cuda):
+    """the kernels' shared-reciprocal division and magic-number floor equal IEEE `/` and (int) casts"""
+    import ctypes
+    from bodyslam_b200 import _lib as L
+    bad = ctypes.c_ulonglong(123)
+    with torch.cuda.device(cuda):
+        L.check(L.load().bslam_selftest(200_000_000, 1234, ctypes.byref(bad), L.stream_ptr(cuda)))
+    assert bad.value == 0, f"{bad.value} mismatches against IEEE division / integer conversion"
+
+
+def test_batch_size_does_not_change_results(cuda):
+    sc = small_scene("laparoscopy512", res=64, frames=12)
+    ref, rc = run_gpu(sc, cuda)
+    from bodyslam_b200 import ops
+    depth = ops.depth_from_u16(sc["depth_u16"], 1000.0, 3.0, cuda)
+    for batch in (1, 5):
+        vol = DenseTSDFVolume(sc["voxel_length"], sc["sdf_trunc"], 64, sc["origin"], color=False, device=cuda)
+        vol.set_batch(batch)
+        vol.integrate_batch(depth, None, sc["intrinsic"], sc["E"])
+        for x, y in zip(ref.export_dense(), vol.export_dense()):
+            assert torch.equal(x, y)
