@@ -34,7 +34,7 @@ def lib():
         L.orc_tsdf_integrate.argtypes = [p, p, p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
                                          p, p, p, C.c_int, C.c_int, p, p, C.c_int]
         L.orc_extract_mesh.argtypes = [p, p, p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, p,
-                                       p, p, p, C.c_int64, p, C.c_int64, p]
+                                       p, p, p, C.c_int64, p, p, C.c_int64, p]
         L.orc_extract_points.restype = C.c_int64
         L.orc_extract_points.argtypes = [p, p, p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, p,
                                          p, p, p, p, C.c_int64]
@@ -124,13 +124,14 @@ class Volume:
             key = np.empty((cap_v, 4), np.int32)
             col = np.empty((cap_v, 3), np.float64) if self.color is not None else None
             t = np.empty((cap_t, 3), np.int32)
+            tz = np.empty(cap_t, np.int32)
             cnt = np.zeros(2, np.int64)
             lib().orc_extract_mesh(_ptr(self.tsdf), _ptr(self.weight), _ptr(self.color), self.nx, self.ny, self.nz,
                                    self.gz0, self.voxel_length, _ptr(self.origin), _ptr(v), _ptr(key), _ptr(col),
-                                   cap_v, _ptr(t), cap_t, _ptr(cnt))
+                                   cap_v, _ptr(t), _ptr(tz), cap_t, _ptr(cnt))
             nv, nt = int(cnt[0]), int(cnt[1])
             if nv <= cap_v and nt <= cap_t:
-                return {"vertices": v[:nv], "keys": key[:nv], "triangles": t[:nt],
+                return {"vertices": v[:nv], "keys": key[:nv], "triangles": t[:nt], "triangle_z": tz[:nt],
                         "colors": None if col is None else col[:nv]}
             cap_v, cap_t = max(cap_v, nv), max(cap_t, nt)
 

@@ -214,13 +214,14 @@ static void map_grow(orc_map *m) {
  * numbered in first-seen order; triangles are (e[t0], e[t2], e[t1]).
  * Outputs (capacity cap_v / cap_t rows; rows beyond capacity are counted, not written):
  *   out_v   [V,3] f64 world position,   out_key [V,4] i32 (x,y,z,axis) local voxel coords,
- *   out_c   [V,3] f64 colour in [0,1] (if color != NULL), out_t [T,3] i32.
+ *   out_c   [V,3] f64 colour in [0,1] (if color != NULL), out_t [T,3] i32,
+ *   out_tz  [T] i32 local z of the emitting cube (optional; lets tests split a mesh into z-slabs).
  * counts[0] = V, counts[1] = T.
  */
 ORC_API void orc_extract_mesh(const float *tsdf, const float *weight, const float *color, int nx,
                               int ny, int nz, int gz0, double voxel_length, const double *origin,
                               double *out_v, int32_t *out_key, double *out_c, int64_t cap_v,
-                              int32_t *out_t, int64_t cap_t, int64_t *counts) {
+                              int32_t *out_t, int32_t *out_tz, int64_t cap_t, int64_t *counts) {
     const double half = voxel_length * 0.5;
     orc_map map; map_init(&map, 1u << 16);
     int64_t nv = 0, nt = 0;
@@ -271,6 +272,7 @@ ORC_API void orc_extract_mesh(const float *tsdf, const float *weight, const floa
                         out_t[3 * nt + 0] = e2v[orc_tri_table[cube_index][i]];
                         out_t[3 * nt + 1] = e2v[orc_tri_table[cube_index][i + 2]];
                         out_t[3 * nt + 2] = e2v[orc_tri_table[cube_index][i + 1]];
+                        if (out_tz) out_tz[nt] = z; /* local z of the cube that emitted the triangle */
                     }
                     ++nt;
                 }

@@ -1,0 +1,135 @@
+"""The C oracle against closed-form expectations of the Open3D semantics it restates (CPU only)."""
+import numpy as np
+import pytest
+
+import oracle
+from bodyslam_b200 import synthetic as S
+
+K = S.K_640
+
+
+def plane_depth(z, H=480, W=640):
+    return np.full((H, W), z, np.float32)
+
+
+def test_depth_from_u16_scale_and_trunc():
+    u = np.array([0, 1, 999, 1000, 2999, 3000, 3001, 65535], np.uint16)
+    d = oracle.o3d.depth_from_u16(u, 1000.0, 3.0)
+    assert d.dtype == np.float32
+    assert np.array_equal(d, np.array([0, np.float32(1) / np.float32(1000), np.float32(999) / np.float32(1000), 1.0,
+                                       np.float32(2999) / np.float32(1000), 0, 0, 0], np.float32))
+
+
+def test_backproject_order_formula_and_inverse_extrinsic():
+    d = np.zeros((4, 5), np.float32)
+    d[1, 2], d[0, 4], d[3, 0] = 2.0, 1.0, 0.5
+    fx, fy, cx, cy = 100.0, 110.0, 2.5, 1.5
+    E = np.eye(4)
+    E[:3, 3] = [0.1, -0.2, 0.3]
+    th = 0.3
+    E[:3, :3] = [[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]]
+    xyz, _ = oracle.o3d.backproject(d, (fx, fy, cx, cy), E)
+    assert xyz.shape == (3, 3)                                   # row-major order of valid pixels
+    want = []
+    for (v, u) in ((0, 4), (1, 2), (3, 0)):
+        z = float(d[v, u])
+        p = np.array([(u - cx) * z / fx, (v - cy) * z / fy, z, 1.0])
+        want.append((np.linalg.inv(E) @ p)[:3])
+    assert np.allclose(xyz, np.array(want), atol=1e-15)
+    full, _ = oracle.o3d.backproject(d, (fx, fy, cx, cy), E, valid_only=False)
+    assert full.shape == (20, 3) and np.isnan(full).all(axis=1).sum() == 17
+    s2, _ = oracle.o3d.backproject(d, (fx, fy, cx, cy), E, stride=2)
+    assert len(s2) == 1                                          # only (0,4) lies on the stride-2 lattice
+
+
+def test_integrate_plane_gives_analytic_tsdf_and_unit_weights():
+    n, vl, trunc = 64, 0.004, 0.02
+    V = oracle.o3d.Volume(n, vl, trunc, origin=(-0.128, -0.128, 0.0))
+    upd = V.integrate(plane_depth(0.15), K, np.eye(4))
+    w, t = V.grid("weight"), V.grid("tsdf")
+    assert upd == int((w == 1).sum()) == V.occupied() and set(np.unique(w)) == {0.0, 1.0}
+    # voxel on the optical axis column: sdf = (d - z) * ray multiplier, truncated to [-1, 1]
+    fx, fy, cx, cy = K
+    ix = iy = 32
+    for iz in range(n):
+        z = (iz + 0.5) * vl
+        x, y = (ix + 0.5) * vl - 0.128, (iy + 0.5) * vl - 0.128
+        uf, vf = x * fx / z + cx + 0.5, y * fy / z + cy + 0.5
+        if not (0.0001 <= uf < 640 - 0.0001 and 0.0001 <= vf < 480 - 0.0001):
+            assert w[ix, iy, iz] == 0                            # projects outside the image
+            continue
+        u, v = int(uf), int(vf)
+        mult = np.sqrt(((u - cx) / fx) ** 2 + ((v - cy) / fy) ** 2 + 1)
+        sdf = (0.15 - z) * mult
+        if sdf > -trunc:
+            assert w[ix, iy, iz] == 1 and abs(t[ix, iy, iz] - min(1.0, sdf / trunc)) < 1e-5
+        else:
+            assert w[ix, iy, iz] == 0
+    # second identical frame: weights 2, tsdf unchanged (running mean of equal values)
+    t0 = t.copy()
+    V.integrate(plane_depth(0.15), K, np.eye(4))
+    assert set(np.unique(V.grid("weight"))) == {0.0, 2.0} and np.abs(V.grid("tsdf") - t0).max() < 1e-6
+
+
+def test_z_restart_modes_and_slab_mode_are_consistent():
+    cfg = S.config("laparoscopy512")
+    E = cfg["extrinsics"](1000)[[10, 500]]
+    depth, _ = S.render(cfg["surface"], E, device="cpu", with_color=False)
+    d = oracle.o3d.depth_from_u16(depth.numpy())
+    args = dict(voxel_length=cfg["voxel_length"] * 8, sdf_trunc=cfg["sdf_trunc"] * 8, origin=cfg["origin"])
+    lit = oracle.o3d.Volume(64, **args)
+    brk = oracle.o3d.Volume(64, **args)
+    for i in range(2):
+        a = lit.integrate(d[i], cfg["K"], E[i], z_restart=0)
+        b = brk.integrate(d[i], cfg["K"], E[i], z_restart=8)
+        assert abs(a - b) <= 0.001 * a
+    same = lit.weight == brk.weight
+    assert same.mean() > 0.9995 and np.abs(lit.tsdf - brk.tsdf)[same].mean() < 1e-5
+    # slab [32, 64) integrated on its own equals the slice of the full volume, in both modes
+    for zr, full in ((8, brk), (0, lit)):
+        slab = oracle.o3d.Volume((64, 64, 32), gz0=32, **args)
+        for i in range(2):
+            slab.integrate(d[i], cfg["K"], E[i], z_restart=zr)
+        assert np.array_equal(slab.grid("weight"), full.grid("weight")[:, :, 32:])
+        assert np.array_equal(slab.grid("tsdf"), full.grid("tsdf")[:, :, 32:])
+
+
+def test_color_running_mean():
+    V = oracle.o3d.Volume(32, 0.008, 0.04, origin=(-0.128, -0.128, 0.0), with_color=True)
+    rgb = np.zeros((480, 640, 3), np.uint8)
+    rgb[..., 0], rgb[..., 1] = 200, 100
+    V.integrate(plane_depth(0.15), K, np.eye(4), rgb=rgb)
+    rgb[..., 0] = 100
+    V.integrate(plane_depth(0.15), K, np.eye(4), rgb=rgb)
+    c = V.color.reshape(-1, 3)[V.weight == 2]
+    assert np.allclose(c, [150, 100, 0])
+    m = V.extract_mesh()
+    assert np.allclose(m["colors"], np.array([150, 100, 0]) / 255.0)
+
+
+def test_mesh_and_points_of_a_plane():
+    n, vl = 48, 0.004
+    V = oracle.o3d.Volume(n, vl, 0.02, origin=(-0.096, -0.096, 0.05))
+    V.integrate(plane_depth(0.15), K, np.eye(4))
+    m = V.extract_mesh()
+    assert len(m["triangles"]) > 500
+    assert np.abs(m["vertices"][:, 2] - 0.15).max() < 2e-4      # ray-distance sdf bends the plane slightly off-axis
+    assert m["triangles"].min() == 0 and m["triangles"].max() == len(m["vertices"]) - 1
+    p = V.extract_points()
+    assert len(p["points"]) > 200 and np.abs(p["points"][:, 2] - 0.15).max() < 2e-4
+    assert np.all(p["normals"][:, 2] < -0.99)                   # towards the camera
+    assert np.all(p["keys"][:, 3] == 2)                         # crossings only along z
+
+
+def test_weight_zero_corner_suppresses_cubes():
+    n = 8
+    V = oracle.o3d.Volume(n, 1.0, 1.0)
+    z = (np.arange(n) + 0.5)[None, None, :] * np.ones((n, n, 1))
+    V.tsdf[:] = np.clip((z - 4.0) / 2, -1, 1).astype(np.float32).reshape(-1)
+    V.weight[:] = 1
+    full = V.extract_mesh()
+    assert len(full["triangles"]) == 2 * (n - 1) ** 2
+    w = V.grid("weight")
+    w[3, 3, 3] = 0                                               # kills the 4 cubes touching it in the crossing layer
+    holed = V.extract_mesh()
+    assert len(holed["triangles"]) == 2 * ((n - 1) ** 2 - 4)
