@@ -206,22 +206,40 @@ def main():
     else:
         depth_u16 = torch.empty((F, H, W), dtype=torch.uint16, device=dev)
     E_dev = torch.as_tensor(E, device=dev).contiguous()
-    z0, z1 = slab_bounds(res, world)[rank]
-    vol = DenseTSDFVolume(vl, trunc, (res, res, z1 - z0), cfg["origin"], color=False, device=dev, gz0=z0, z_total=res)
+    # N > 1: round-robin brick layers (rank r owns every N-th 8-voxel layer) -> balanced whatever the view
+    interleaved = world > 1 and (res // 8) % world == 0
+    if interleaved:
+        vol = DenseTSDFVolume(vl, trunc, (res, res, res // world), cfg["origin"], color=False, device=dev, gz0=8 * rank, z_total=res,
+                              z_interleave=world)
+    else:
+        z0, z1 = slab_bounds(res, world)[rank]
+        vol = DenseTSDFVolume(vl, trunc, (res, res, z1 - z0), cfg["origin"], color=False, device=dev, gz0=z0, z_total=res)
     if args.batch:
         vol.set_batch(args.batch)
     depth_f = torch.empty((F, H, W), dtype=torch.float32, device=dev)
     L = _lib.load()
 
-    def a4(src_u16):
-        _lib.check(L.bslam_depth_from_u16(_lib.ptr(src_u16), src_u16.numel(), 1000.0, 3.0, _lib.ptr(depth_f), _lib.stream_ptr(dev)))
+    def a4(src_u16, dst_f32):
+        _lib.check(L.bslam_depth_from_u16(_lib.ptr(src_u16), src_u16.numel(), 1000.0, 3.0, _lib.ptr(dst_f32), _lib.stream_ptr(dev)))
+
+    chunk = args.batch or 256
+    chunks = [(f0, min(F, f0 + chunk)) for f0 in range(0, F, chunk)]
 
     def step(src_u16, counts=None):
-        if world > 1:
-            dist.broadcast(src_u16.view(torch.int16), 0)
-            dist.broadcast(E_dev, 0)
-        a4(src_u16)
-        vol.integrate_batch(depth_f, None, intr, E, update_counts=counts)
+        if world == 1:
+            a4(src_u16, depth_f)
+            vol.integrate_batch(depth_f, None, intr, E, update_counts=counts)
+            return
+        # rank 0 holds the frames: broadcast chunk k+1 over NCCL while chunk k is integrated
+        dist.broadcast(E_dev, 0)
+        u8 = src_u16.view(torch.uint8)  # NCCL has no 16-bit integer type: ship the bytes
+        work = dist.broadcast(u8[chunks[0][0]:chunks[0][1]], 0, async_op=True)
+        for k, (f0, f1) in enumerate(chunks):
+            work.wait()
+            if k + 1 < len(chunks):
+                work = dist.broadcast(u8[chunks[k + 1][0]:chunks[k + 1][1]], 0, async_op=True)
+            a4(src_u16[f0:f1], depth_f[f0:f1])
+            vol.integrate_batch(depth_f[f0:f1], None, intr, E[f0:f1], update_counts=None if counts is None else counts[f0:f1])
 
     def barrier():
         if world > 1:
@@ -237,8 +255,8 @@ def main():
 
     # ---- algorithmic bytes: U_f = voxels each frame updates (dry run, untimed), summed over slabs
     if world > 1:
-        dist.broadcast(depth_u16.view(torch.int16), 0)
-    a4(depth_u16)
+        dist.broadcast(depth_u16.view(torch.uint8), 0)
+    a4(depth_u16, depth_f)
     uf_local = vol.count_updates(depth_f, intr, E)
     uf = uf_local.clone()
     if world > 1:
@@ -273,14 +291,18 @@ def main():
     host_counts = torch.empty(F, dtype=torch.int64).pin_memory()
     if rank == 0:
         host_u16.copy_(depth_u16)
-    stage_u16 = torch.empty_like(depth_u16)
     counts = torch.zeros(F, dtype=torch.int64, device=dev)
+    stage_u16 = torch.empty_like(depth_u16) if world > 1 else None
 
     def e2e_step():
-        if rank == 0:
-            stage_u16.copy_(host_u16, non_blocking=True)
         counts.zero_()
-        step(stage_u16, counts)
+        if world == 1:
+            # public API: pinned host frames in, per-frame update counts out (H2D overlapped with compute)
+            vol.integrate_host(host_u16, None, intr, E, depth_scale=1000.0, depth_trunc=3.0, update_counts=counts)
+        else:
+            if rank == 0:
+                stage_u16.copy_(host_u16, non_blocking=True)
+            step(stage_u16, counts)
         host_counts.copy_(counts, non_blocking=True)
 
     e2e_step()
@@ -342,7 +364,7 @@ def main():
                                    f"sdf_trunc {trunc * 1e3:g} mm (BASELINE configs[3])",
                        "frames_per_step": F, "step": "a4 depth scaling + K3 integrate of all frames, volume resident",
                        "l2": "inputs larger than L2 (1.2 GB depth + 1.1 GB volume per step vs 126 MB)",
-                       "parallelism": f"z-slab x{world}" if world > 1 else "single GPU",
+                       "parallelism": (f"round-robin brick-layer z-shards x{world}" if interleaved else f"z-slab x{world}") if world > 1 else "single GPU",
                        "voxels_updated_per_frame": uf_total / F, **extras},
             "clocks": clocks,
             "e2e": {"value": fps_e2e, "unit": UNIT, "h2d_bytes_per_step": F * H * W * 2 + F * 128, "d2h_bytes_per_step": F * 8},

@@ -42,7 +42,8 @@ struct VolView {
     float2 *vox;
     float *color;        // optional: per brick 3 planes of 512 f32 (r, g, b)
     uint8_t *flags;      // per brick: 1 once any voxel of the brick was updated
-    int nx, ny, nz, gz0; // logical box
+    int nx, ny, nz, gz0; // logical box; global z of local plane z = gz0 + (z / 8) * 8 * zs + z % 8
+    int zs;              // z interleave stride in brick layers (1 = contiguous slab, N = round-robin over N ranks)
     int nbx, nby, nbz;   // bricks per axis (ceil)
     float vl, half, trunc, trunc_inv;
     double ox, oy, oz;

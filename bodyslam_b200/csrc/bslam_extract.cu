@@ -388,6 +388,7 @@ extern "C" {
 
 int bslam_mc_count(bslam_volume *vol, const float *d_halo_lo, const float *d_halo_hi, int64_t *h_counts, bslam_stream_t stream) {
     BSLAM_CHECK_ARG(vol && h_counts, "bslam_mc_count: NULL argument");
+    BSLAM_CHECK_ARG(vol->v.zs == 1, "bslam_mc_count: interleaved slabs must be re-sharded to contiguous ones first");
     BSLAM_CUDA(cudaSetDevice(vol->device));
     int rc = ensure_mc_scratch(vol);
     if (rc) return rc;
@@ -422,7 +423,7 @@ int bslam_mc_emit(bslam_volume *vol, const float *d_halo_lo, const float *d_halo
 
 int bslam_points_count(bslam_volume *vol, int64_t *h_count, bslam_stream_t stream) {
     BSLAM_CHECK_ARG(vol && h_count, "bslam_points_count: NULL argument");
-    BSLAM_CHECK_ARG(vol->v.gz0 == 0, "bslam_points_count: single-box volumes only (gz0 must be 0)");
+    BSLAM_CHECK_ARG(vol->v.gz0 == 0 && vol->v.zs == 1, "bslam_points_count: single-box volumes only (gz0 must be 0)");
     BSLAM_CUDA(cudaSetDevice(vol->device));
     int rc = ensure_mc_scratch(vol);
     if (rc) return rc;

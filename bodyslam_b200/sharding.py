@@ -87,7 +87,12 @@ def broadcast_frames(depth, color, extrinsics, src: int = 0, group=None):
     tensor [F,4,4] on the same device.  Returns the tensors (filled in place)."""
     import torch.distributed as dist
 
-    works = [dist.broadcast(depth, src, group=group, async_op=True)]
+    import torch
+
+    if depth.dtype == torch.uint16:  # NCCL has no 16-bit integer type: ship the bytes
+        works = [dist.broadcast(depth.view(torch.uint8), src, group=group, async_op=True)]
+    else:
+        works = [dist.broadcast(depth, src, group=group, async_op=True)]
     if color is not None:
         works.append(dist.broadcast(color, src, group=group, async_op=True))
     works.append(dist.broadcast(extrinsics, src, group=group, async_op=True))
@@ -157,15 +162,64 @@ def gather_meshes(mesh: TriangleMesh, rank: int, world_size: int, dst: int = 0, 
     return out
 
 
-class ShardedTSDF:
-    """One z-slab of a dense TSDF per rank; same surface as `TSDF` for integration, mesh on rank 0.
+def reshard_plan(n_layers: int, world_size: int, rank: int):
+    """Round-robin -> contiguous re-sharding of brick layers.
 
+    Interleaved rank r holds global layers g = l * world_size + r (local index l); contiguous rank
+    q holds g in [q * L, (q + 1) * L), L = n_layers / world_size.  Returns (send, recv): send[q] =
+    my local interleaved indices that go to rank q (ascending); recv[p] = the local contiguous
+    indices at which the layers coming from rank p land (same order as p sends them).
+    """
+    if n_layers % world_size:
+        raise ValueError("interleaved sharding needs a brick-layer count divisible by the world size")
+    L = n_layers // world_size
+    send = [[l for l in range(L) if q * L <= l * world_size + rank < (q + 1) * L] for q in range(world_size)]
+    recv = [[l * world_size + p - rank * L for l in range(L) if rank * L <= l * world_size + p < (rank + 1) * L]
+            for p in range(world_size)]
+    return send, recv
+
+
+def reshard_layers(src_layers, dst_layers, send, recv, group=None):
+    """all-to-all of whole brick layers: src_layers / dst_layers are [n_local_layers, bytes] uint8
+    views (interleaved source, contiguous destination)."""
+    import torch
+    import torch.distributed as dist
+
+    dev = src_layers.device
+    rank = dist.get_rank(group)
+    ins = [src_layers[torch.as_tensor(ix, dtype=torch.long, device=dev)].contiguous() for ix in send]
+    outs = [torch.empty((len(ix), src_layers.shape[1]), dtype=src_layers.dtype, device=dev) for ix in recv]
+    ops_ = []
+    for p in range(len(send)):     # point-to-point pairs (NCCL groups them; gloo has no all_to_all)
+        if p == rank:
+            outs[p].copy_(ins[p])
+            continue
+        if ins[p].numel():
+            ops_.append(dist.P2POp(dist.isend, ins[p], p, group))
+        if outs[p].numel():
+            ops_.append(dist.P2POp(dist.irecv, outs[p], p, group))
+    if ops_:
+        for w in dist.batch_isend_irecv(ops_):
+            w.wait()
+    for buf, ix in zip(outs, recv):
+        if ix:
+            dst_layers[torch.as_tensor(ix, dtype=torch.long, device=dev)] = buf
+
+
+class ShardedTSDF:
+    """One z-shard of a dense TSDF per rank; same surface as `TSDF` for integration, mesh on rank 0.
+
+    layout="interleaved" (default when possible): rank r owns every world_size-th 8-voxel brick
+    layer -- every rank sees the same share of any frustum, so integration scales whatever the
+    camera looks at.  Extraction first re-shards the brick layers into contiguous slabs (one
+    all-to-all over NVLink), then exchanges one halo plane per slab boundary.
+    layout="contiguous": plain z-slabs (no re-shard, but the load follows the scene).
     Every rank calls every method (SPMD).  `integrate_batch` is collective-free; pass
     `broadcast_from=0` when only rank 0 holds the frames.
     """
 
     def __init__(self, voxel_length=0.001, sdf_trunc=0.1, resolution=512, origin=None, color=True, device=None,
-                 rank=None, world_size=None, group=None):
+                 rank=None, world_size=None, group=None, layout="interleaved"):
         import torch.distributed as dist
 
         from .tsdf import DenseTSDFVolume
@@ -177,11 +231,20 @@ class ShardedTSDF:
             resolution = (int(resolution),) * 3
         self.nx, self.ny, self.nz = resolution
         self.bounds = slab_bounds(self.nz, self.world_size)
-        z0, z1 = self.bounds[self.rank]
         if origin is None:
             origin = tuple(-0.5 * n * voxel_length for n in resolution)
-        self.tsdf = DenseTSDFVolume(voxel_length, sdf_trunc, (self.nx, self.ny, z1 - z0), origin, color=color, device=device,
-                                    gz0=z0, z_total=self.nz)
+        self._args = dict(voxel_length=voxel_length, sdf_trunc=sdf_trunc, origin=origin, color=color, device=device)
+        n_layers = self.nz // BRICK
+        if self.world_size == 1 or self.nz % BRICK or n_layers % self.world_size:
+            layout = "contiguous"
+        self.layout = layout
+        if layout == "interleaved":
+            self.tsdf = DenseTSDFVolume(voxel_length, sdf_trunc, (self.nx, self.ny, self.nz // self.world_size), origin, color=color,
+                                        device=device, gz0=BRICK * self.rank, z_total=self.nz, z_interleave=self.world_size)
+        else:
+            z0, z1 = self.bounds[self.rank]
+            self.tsdf = DenseTSDFVolume(voxel_length, sdf_trunc, (self.nx, self.ny, z1 - z0), origin, color=color, device=device,
+                                        gz0=z0, z_total=self.nz)
 
     def integrate_batch(self, depth, color, intrinsic, extrinsics, broadcast_from=None):
         if broadcast_from is not None and self.world_size > 1:
@@ -195,11 +258,27 @@ class ShardedTSDF:
     def build_3D_map(self, rgbd, intrinsic, extrinsic):
         self.tsdf.integrate(rgbd, intrinsic, extrinsic)
 
+    def contiguous_slab(self):
+        """this rank's contiguous z-slab as a DenseTSDFVolume (re-sharded copy in interleaved mode)"""
+        if self.layout != "interleaved":
+            return self.tsdf
+        from .tsdf import DenseTSDFVolume
+
+        z0, z1 = self.bounds[self.rank]
+        a = self._args
+        slab = DenseTSDFVolume(a["voxel_length"], a["sdf_trunc"], (self.nx, self.ny, z1 - z0), a["origin"], color=a["color"],
+                               device=self.tsdf.device, gz0=z0, z_total=self.nz)
+        send, recv = reshard_plan(self.nz // BRICK, self.world_size, self.rank)
+        src, dst = self.tsdf.storage_layers(), slab.storage_layers()
+        for k in src:
+            reshard_layers(src[k], dst[k], send, recv, self.group)
+        return slab
+
     def extract_mesh(self):
         """full mesh on rank 0 (None on the other ranks)"""
-        v = self.tsdf
         if self.world_size == 1:
-            return v.extract_triangle_mesh()
+            return self.tsdf.extract_triangle_mesh()
+        v = self.contiguous_slab()
         lo, hi = exchange_halo_planes(v.export_plane(v.nz - 1), v.export_plane(0), self.rank, self.world_size, self.group)
         mesh = v.extract_triangle_mesh(halo_lo=lo, halo_hi=hi)
         parts = gather_meshes(mesh, self.rank, self.world_size, 0, self.group)

@@ -142,9 +142,5 @@ def update_map_after_pg(global_extrinsic, list_of_rgb, list_of_depth, depth_scal
     dev = tsdf.tsdf.device
     depth_u16, rgb = load_frames(list_of_rgb, list_of_depth, n, depth_scale, 3.0, dev)
     E = np.stack([np.asarray(to_numpy(e), dtype=np.float64) for e in global_extrinsic])
-    chunk = 256
-    for i0 in range(0, n, chunk):
-        d = ops.depth_from_u16(depth_u16[i0:i0 + chunk].to(dev, non_blocking=True), depth_scale, 3.0, dev)
-        c = rgb[i0:i0 + chunk].to(dev, non_blocking=True) if tsdf.tsdf.color else None
-        tsdf.tsdf.integrate_batch(d, c, intrinsic, E[i0:i0 + chunk])
+    tsdf.tsdf.integrate_host(depth_u16, rgb if tsdf.tsdf.color else None, intrinsic, E, depth_scale=depth_scale, depth_trunc=3.0)
     return tsdf

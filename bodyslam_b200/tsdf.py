@@ -31,7 +31,7 @@ class DenseTSDFVolume:
     """
 
     def __init__(self, voxel_length: float, sdf_trunc: float, resolution=512, origin=None, color: bool = True,
-                 device=None, gz0: int = 0, z_total: int | None = None):
+                 device=None, gz0: int = 0, z_total: int | None = None, z_interleave: int = 1):
         torch = _lib.require_cuda()
         self._L = _lib.load()
         self.device = ops._device(device)
@@ -53,7 +53,23 @@ class DenseTSDFVolume:
             _lib.check(self._L.bslam_tsdf_create(C.byref(self._h), self.nx, self.ny, self.nz, self.gz0, self.voxel_length,
                                                  self.sdf_trunc, _lib.ptr(self.origin), int(self.color), self.device.index,
                                                  _lib.ptr(self._storage), _lib.stream_ptr(self.device)))
+        self.z_interleave = int(z_interleave)
+        if self.z_interleave != 1:
+            _lib.check(self._L.bslam_tsdf_set_z_interleave(self._h, self.z_interleave))
         self.frames_integrated = 0
+
+    def storage_layers(self):
+        """views of the storage as brick layers: dict(vox [nbz, bytes], flags [nbz, nbx*nby][, color [nbz, bytes]]).
+        A brick layer (all bricks with one bz) is contiguous in each region -- the unit z-re-sharding moves."""
+        off = (C.c_size_t * 4)()
+        _lib.check(self._L.bslam_tsdf_layout(self._h, off))
+        nbx, nby, nbz = (self.nx + 7) // 8, (self.ny + 7) // 8, (self.nz + 7) // 8
+        nb = nbx * nby * nbz
+        out = {"vox": self._storage[off[0]:off[0] + nb * 4096].view(nbz, nbx * nby * 4096),
+               "flags": self._storage[off[2]:off[2] + nb].view(nbz, nbx * nby)}
+        if self.color:
+            out["color"] = self._storage[off[1]:off[1] + nb * 6144].view(nbz, nbx * nby * 6144)
+        return out
 
     # ------------------------------------------------------------------ lifetime
     def __del__(self):
@@ -69,7 +85,7 @@ class DenseTSDFVolume:
         """`deepcopy(self.tsdf)` of tsdf.py:24 -> device-to-device clone."""
         torch = _lib.require_cuda()
         other = DenseTSDFVolume(self.voxel_length, self.sdf_trunc, (self.nx, self.ny, self.nz), self.origin, self.color,
-                                self.device, self.gz0, self.z_total)
+                                self.device, self.gz0, self.z_total, self.z_interleave)
         with torch.cuda.device(self.device):
             _lib.check(self._L.bslam_tsdf_copy(self._h, other._h, _lib.stream_ptr(self.device)))
         other.frames_integrated = self.frames_integrated
@@ -135,6 +151,61 @@ class DenseTSDFVolume:
                                                     _lib.stream_ptr(self.device)))
         if not dry_run:
             self.frames_integrated += F
+
+    def integrate_host(self, depth_u16, color, intrinsic, extrinsics, depth_scale: float = 1000.0, depth_trunc: float = 3.0,
+                       chunk: int = 256, update_counts=None):
+        """Frames that live in HOST memory (ideally pinned): uint16 depth [F,H,W] (+ uint8 colour
+        [F,H,W,3]) are streamed to the device in chunks on a side stream, double-buffered, while
+        the previous chunk is converted (a4) and integrated (K3) on the current stream -- the
+        shape of `update_map_after_pg` once the PNGs are decoded.  Frame order is preserved.
+        """
+        torch = _lib.require_cuda()
+        if ops._dtype_name(depth_u16) != "uint16":
+            raise RuntimeError("[DenseTSDFVolume::IntegrateHost] Unsupported image format.")
+        if not hasattr(depth_u16, "is_cuda"):
+            depth_u16 = torch.from_numpy(np.ascontiguousarray(to_numpy(depth_u16)))
+        if color is not None and not hasattr(color, "is_cuda"):
+            color = torch.from_numpy(np.ascontiguousarray(to_numpy(color)))
+        F, H, W = depth_u16.shape
+        E = np.asarray(to_numpy(extrinsics), dtype=np.float64).reshape(-1, 4, 4)
+        use_color = self.color and color is not None
+        if self.color and color is None:
+            raise RuntimeError("[DenseTSDFVolume::IntegrateHost] Unsupported image format.")
+        dev = self.device
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream(dev)
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(dev)
+            cs = self._copy_stream
+            n = min(chunk, F)
+            key = (n, H, W, use_color)
+            if getattr(self, "_stage_key", None) != key:
+                self._stage = [(torch.empty((n, H, W), dtype=torch.uint16, device=dev),
+                                torch.empty((n, H, W), dtype=torch.float32, device=dev),
+                                torch.empty((n, H, W, 3), dtype=torch.uint8, device=dev) if use_color else None)
+                               for _ in range(2)]
+                self._stage_key = key
+            free = [None, None]      # event: the compute stream is done with staging buffer i
+            cs.wait_stream(main)
+            for k, f0 in enumerate(range(0, F, n)):
+                f1 = min(F, f0 + n)
+                m = f1 - f0
+                u16, f32, col = self._stage[k & 1]
+                with torch.cuda.stream(cs):
+                    if free[k & 1] is not None:
+                        cs.wait_event(free[k & 1])
+                    u16[:m].copy_(depth_u16[f0:f1], non_blocking=True)
+                    if use_color:
+                        col[:m].copy_(color[f0:f1], non_blocking=True)
+                    copied = torch.cuda.Event()
+                    copied.record(cs)
+                main.wait_event(copied)
+                _lib.check(self._L.bslam_depth_from_u16(_lib.ptr(u16), m * H * W, float(depth_scale), float(depth_trunc or 0.0),
+                                                        _lib.ptr(f32), _lib.stream_ptr(dev)))
+                self.integrate_batch(f32[:m], col[:m] if use_color else None, intrinsic, E[f0:f1],
+                                     update_counts=None if update_counts is None else update_counts[f0:f1])
+                free[k & 1] = torch.cuda.Event()
+                free[k & 1].record(main)
 
     def count_updates(self, depth, intrinsic, extrinsics, zmarch: int = _lib.ZMARCH_BRICK):
         """U_f of SURVEY.md 8(d): voxels each frame WOULD update (volume untouched) -> i64 [F]."""

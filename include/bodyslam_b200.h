@@ -160,6 +160,16 @@ BSLAM_API int bslam_tsdf_integrate(bslam_volume *vol, const float *d_depth, cons
                                    unsigned long long *d_update_counts, int dry_run,
                                    bslam_stream_t stream);
 
+/* Round-robin z-sharding: this box holds every `stride_bricks`-th 8-voxel brick layer of the
+ * grid, starting at global plane gz0 (= 8 * rank): local plane z is global plane
+ * gz0 + (z / 8) * 8 * stride_bricks + z % 8.  Balances integration across ranks whatever the
+ * camera looks at; extraction needs contiguous slabs again (re-shard brick layers first, see
+ * bodyslam_b200/sharding.py).  stride_bricks = 1 (default) is a contiguous slab. */
+BSLAM_API int bslam_tsdf_set_z_interleave(bslam_volume *vol, int stride_bricks);
+/* byte offsets {voxels, colour, brick flags, total} inside the storage buffer; a brick layer
+ * (all bricks of one bz) is contiguous in each region, which is what re-sharding moves */
+BSLAM_API int bslam_tsdf_layout(const bslam_volume *vol, size_t *h_offsets /* [4] */);
+
 /* frames per integrate launch (1..BSLAM_MAX_BATCH, 0 = library default).  Larger batches keep a
  * voxel in registers across more frames; smaller ones keep the batch's depth images L2-resident. */
 BSLAM_API int bslam_tsdf_set_batch(bslam_volume *vol, int frames_per_launch);

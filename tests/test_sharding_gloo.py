@@ -11,7 +11,8 @@ import torch.multiprocessing as mp
 
 import oracle
 from bodyslam_b200.geometry import TriangleMesh
-from bodyslam_b200.sharding import (broadcast_frames, exchange_halo_planes, gather_meshes, merge_slab_meshes, slab_bounds)
+from bodyslam_b200.sharding import (broadcast_frames, exchange_halo_planes, gather_meshes, merge_slab_meshes, reshard_layers,
+                                    reshard_plan, slab_bounds)
 from util import canon_mesh
 
 
@@ -24,6 +25,25 @@ def test_slab_bounds():
     assert all(z0 % 8 == 0 for z0, _ in b)
     with pytest.raises(ValueError):
         slab_bounds(16, 3)
+
+
+def test_reshard_plan_is_a_permutation():
+    for world in (2, 4, 8):
+        n = 64
+        L = n // world
+        plans = [reshard_plan(n, world, r) for r in range(world)]
+        for q in range(world):
+            got = []
+            for p in range(world):
+                send_pq = plans[p][0][q]                  # local interleaved indices rank p sends to q
+                recv_qp = plans[q][1][p]                  # where rank q stores them
+                assert len(send_pq) == len(recv_qp)
+                for l, dst in zip(send_pq, recv_qp):
+                    assert l * world + p == q * L + dst   # same global layer on both sides
+                got += recv_qp
+            assert sorted(got) == list(range(L))
+    with pytest.raises(ValueError):
+        reshard_plan(10, 4, 0)
 
 
 def field(n=40, seed=5):
@@ -99,6 +119,14 @@ def _worker(rank, world, port, ret):
         E = torch.eye(4, dtype=torch.float64).repeat(2, 1, 1) * (rank + 1)
         broadcast_frames(depth, color, E, src=0)
         assert float(depth.max()) == 0.0 and int(color.max()) == 0 and float(E[0, 0, 0]) == 1.0
+        # round-robin -> contiguous re-shard of (fake) brick layers: layer g is filled with the value g
+        if 12 % world == 0:
+            Lh = 12 // world
+            src = torch.stack([torch.full((5,), l * world + rank, dtype=torch.uint8) for l in range(Lh)])
+            dst = torch.zeros((Lh, 5), dtype=torch.uint8)
+            send, recv = reshard_plan(12, world, rank)
+            reshard_layers(src, dst, send, recv)
+            assert dst[:, 0].tolist() == list(range(rank * Lh, (rank + 1) * Lh))
         # mesh gather + merge on rank 0
         parts = gather_meshes(mine, rank, world, dst=0)
         if rank == 0:
