@@ -70,7 +70,7 @@ class RGBD:
         self.depth_path = depth_path
         self.depth_scale = depth_scale
         self.depth_trunc = depth_trunc
-        self.device = ops._device(device if (device is not None and "cuda" in str(device).lower()) else None)
+        self.device = ops._device(str(device).lower() if (device is not None and "cuda" in str(device).lower()) else None)
 
         depth_u16 = cv2.imread(depth_path, cv2.IMREAD_ANYDEPTH)
         if depth_u16 is None or depth_u16.dtype != np.uint16:

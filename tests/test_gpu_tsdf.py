@@ -205,3 +205,42 @@ def test_batch_size_does_not_change_results(cuda):
         vol.integrate_batch(depth, None, sc["intrinsic"], sc["E"])
         for x, y in zip(ref.export_dense(), vol.export_dense()):
             assert torch.equal(x, y)
+
+
+def test_rgbd_loader_and_update_map_after_pg_from_png_files(cuda, tmp_path):
+    """a4 + a11 through the reference's file-based entry points (slam_utils.py:124-135,172-264)"""
+    import cv2
+    from bodyslam_b200.slam_utils import RGBD, update_map_after_pg
+    sc = small_scene("laparoscopy512", res=64, frames=5)
+    rgb_paths, depth_paths = [], []
+    for i in range(5):
+        rp, dp = str(tmp_path / f"rgb_{i}.png"), str(tmp_path / f"depth_{i}.png")
+        cv2.imwrite(rp, sc["color"][i][:, :, ::-1])
+        cv2.imwrite(dp, sc["depth_u16"][i])
+        rgb_paths.append(rp); depth_paths.append(dp)
+    fr = RGBD(rgb_paths[0], depth_paths[0], device="CUDA:0", depth_scale=1000, depth_trunc=3.0)
+    ref_d = oracle.o3d.depth_from_u16(sc["depth_u16"][0])
+    assert (fr.height, fr.width) == (sc["H"], sc["W"])
+    assert np.array_equal(fr.rgbd_tsdf.depth.cpu().numpy(), ref_d)
+    assert np.array_equal(fr.rgbd_tsdf.color.cpu().numpy(), sc["color"][0])
+    cvd = sc["depth_u16"][0].astype(np.float32) / 1000
+    assert np.array_equal(fr.cv2_depth.cpu().numpy(), cvd) and fr.depth_min == float(cvd.min()) and fr.depth_max == float(cvd.max())
+    jet = cv2.applyColorMap(oracle.mdem.minmax_u8(sc["depth_u16"][0]), cv2.COLORMAP_JET)
+    assert np.array_equal(fr.colored_depth.cpu().numpy(), jet)
+    tsdf = update_map_after_pg(list(sc["E"]), rgb_paths, depth_paths, 1000, "CUDA:0", sc["intrinsic"],
+                               voxel_length=sc["voxel_length"], sdf_trunc=sc["sdf_trunc"], resolution=64, origin=sc["origin"])
+    V, _ = run_oracle(sc, color=True)
+    assert_volume_equal(tsdf.tsdf, V, sc["sdf_trunc"], color=True)
+    # frame-by-frame through the drop-in classes gives the same map
+    t2 = TSDF(voxel_length=sc["voxel_length"], sdf_trunc=sc["sdf_trunc"], resolution=64, origin=sc["origin"], device=cuda)
+    for i in range(5):
+        t2.build_3D_map(RGBD(rgb_paths[i], depth_paths[i], "CUDA:0").rgbd_tsdf, sc["intrinsic"], sc["E"][i])
+    for x, y in zip(tsdf.tsdf.export_dense(True), t2.tsdf.export_dense(True)):
+        assert torch.equal(x, y)
+    pcd = t2.extract_pcd()
+    mesh = t2.extract_mesh()
+    assert pcd.points.shape[0] > 100 and mesh.triangles.shape[0] > 100 and mesh.vertex_colors is not None
+    t2.save_mesh(str(tmp_path / "m.ply")); t2.save_pcd(str(tmp_path / "p.ply"))
+    from bodyslam_b200.io import read_ply
+    v, f = read_ply(str(tmp_path / "m.ply"))
+    assert len(v) == mesh.vertices.shape[0] and len(f) == mesh.triangles.shape[0]
