@@ -34,7 +34,7 @@ WORKLOAD = "laparoscopy512"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--frames", type=int, default=0, help="frames per step (default: the config's 1000)")
@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--no-mc", action="store_true")
     ap.add_argument("--batch", type=int, default=0, help="frames per integrate launch (0 = library default)")
     ap.add_argument("--color", action="store_true", help="also integrate RGB8 colour (reported as an extra, not the headline)")
+    ap.add_argument("--extras", action="store_true", help="also time K1/K2 on BASELINE configs[2] (64 x 1080p) and point extraction")
     return ap.parse_args()
 
 
@@ -56,48 +57,75 @@ def load_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def load_traffic(args, world, res, F):
+    """DRAM bytes per brick_integrate_kernel launch from the committed `ncu --set full` capture
+    (profiles/traffic.json); only quoted when this run has the captured run's shape."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(p))["brick_integrate_kernel"]
+    except Exception:
+        return None, None
+    if world != t.get("n_gpus", 1) or res != t.get("resolution") or (args.batch or 256) != t.get("frames_per_launch") or F != t.get("frames"):
+        return None, "profiles/traffic.json holds a different configuration"
+    return t["dram_bytes_per_launch"], t["source"]
+
+
 class ClockSampler:
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi polled every 25 ms for the whole run; only samples whose timestamp falls inside a
+    timed window (resident / e2e loops) are reported, so the clocks are the ones under load."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.p = None
+        self.windows = []
         self.path = f"/tmp/bslam_clocks_{os.getpid()}.csv"
         try:
             self.f = open(self.path, "w")
-            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "25", "-i", str(index)],
                                       stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
 
+    def window(self, t0, t1):
+        self.windows.append((t0, t1))
+
     def stop(self):
+        import datetime
+
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if self.p is None:
             return out
+        time.sleep(0.06)
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
         except Exception:
             self.p.kill()
         self.f.close()
-        sm, mx, reasons = [], [], set()
+        rows = []
         for line in open(self.path):
             t = [x.strip() for x in line.split(",")]
-            if len(t) < 7:
+            if len(t) < 8:
                 continue
             try:
-                sm.append(float(t[0])); mx.append(float(t[1]))
+                ts = datetime.datetime.strptime(t[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(t[1]), float(t[2]), [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                                                                 "sw_power_cap"), t[4:8]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), t[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
         try:
             os.remove(self.path)
         except OSError:
             pass
-        if sm:
-            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        inside = [r for r in rows if any(a - 0.005 <= r[0] <= b + 0.005 for a, b in self.windows)]
+        where = "inside the timed regions"
+        if not inside and rows and self.windows:   # timed regions shorter than the poll period: nearest sample to each window
+            inside = [min(rows, key=lambda r: abs(r[0] - 0.5 * (a + b))) for a, b in self.windows]
+            where = "nearest to the timed regions (regions shorter than the 25 ms poll period)"
+        if inside:
+            out.update(sm_mhz=float(np.median([r[1] for r in inside])), sm_max_mhz=float(max(r[2] for r in inside)),
+                       reasons=sorted({n for r in inside for n in r[3]}), samples=len(inside), sampled=where)
         return out
 
 
@@ -266,19 +294,21 @@ def main():
     bytes_algo_local = 16 * int(uf_local.sum().item()) + 4 * W * H * F
 
     # ---- device-resident timing
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
         step(depth_u16)
     vol.profile(True)
-    sampler = ClockSampler(local) if rank == 0 else None
     barrier()
+    tw0 = time.time()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
     for _ in range(args.steps):
         step(depth_u16)
     ev1.record()
     barrier()
+    if sampler:
+        sampler.window(tw0, time.time())
     ms_total = max_over_ranks(ev0.elapsed_time(ev1))
-    clocks = sampler.stop() if sampler else None
     k_ms, k_launches = vol.profile_read()
     vol.profile(False)
     fps = args.steps * F / (ms_total / 1e3)
@@ -307,12 +337,16 @@ def main():
 
     e2e_step()
     barrier()
+    tw0 = time.time()
     ev0.record()
     for _ in range(args.steps):
         e2e_step()
     ev1.record()
     barrier()
+    if sampler:
+        sampler.window(tw0, time.time())
     ms_e2e = max_over_ranks(ev0.elapsed_time(ev1))
+    clocks = sampler.stop() if sampler else None   # samples inside both timed regions (resident + e2e)
     fps_e2e = args.steps * F / (ms_e2e / 1e3)
     if rank == 0:
         print(f"[bench] e2e: {fps_e2e:.1f} frames/s, {ms_e2e / args.steps:.2f} ms/step", file=sys.stderr)
@@ -327,18 +361,63 @@ def main():
         extras["mc_ms"] = 1e3 * (time.perf_counter() - t0)
         extras["mc_vertices"], extras["mc_triangles"] = int(mesh.vertices.shape[0]), int(mesh.triangles.shape[0])
         del mesh
-    if args.color and world == 1:
+    if (args.color or args.extras) and world == 1:
         _, col = S.render(cfg["surface"], E[:64], K=cfg["K"], W=W, H=H, device=dev, with_color=True)
         cvol = DenseTSDFVolume(vl, trunc, res, cfg["origin"], color=True, device=dev)
         for _ in range(2):
             cvol.integrate_batch(depth_f[:64], col, intr, E[:64])
         torch.cuda.synchronize()
         ev0.record()
-        cvol.integrate_batch(depth_f[:64], col, intr, E[:64])
+        for _ in range(4):
+            cvol.integrate_batch(depth_f[:64], col, intr, E[:64])
         ev1.record()
         torch.cuda.synchronize()
-        extras["fps_rgb8_64frames"] = 64 / (ev0.elapsed_time(ev1) / 1e3)
+        extras["fps_rgb8_64frame_batches"] = 4 * 64 / (ev0.elapsed_time(ev1) / 1e3)
         del cvol, col
+    if args.extras and world == 1:
+        from bodyslam_b200 import mdem
+
+        def timed(fn, n=5):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            ev0.record()
+            for _ in range(n):
+                fn()
+            ev1.record()
+            torch.cuda.synchronize()
+            return ev0.elapsed_time(ev1) / n
+
+        # BASELINE configs[2]: 64-frame batched 1080p depth scale + colorize + back-project
+        B, Hh, Ww = 64, 1080, 1920
+        g = torch.Generator(device=dev).manual_seed(0)
+        metres = 0.3 + 2.5 * torch.rand((B, Hh, Ww), device=dev, generator=g)
+        metres[:, ::7, ::5] = 0.0
+        lut = mdem.get_cmap_lut("viridis")
+        ms = timed(lambda: ops.colorize_u16(lut, depth_m=metres, invalid_val=0))
+        px = B * Hh * Ww
+        extras["k1_colorize_1080p_x64"] = {"ms": ms, "frames_per_s": B / (ms / 1e3), "algorithmic_GBps": 10 * px / 1e9 / (ms / 1e3),
+                                           "frac_of_hbm_peak": 10 * px / 1e9 / (ms / 1e3) / load_peaks()[0]}
+        K1080 = tuple(k * 3.0 for k in cfg["K"])
+        Eb = E[:B]
+        res_bp = {}
+
+        def bp():
+            res_bp["xyz"], _ = ops.backproject(metres, K1080, Eb)
+
+        ms = timed(bp, 3)
+        nvalid = int(res_bp["xyz"].shape[0])
+        by = 4 * px + 12 * nvalid
+        extras["k2_backproject_1080p_x64"] = {"ms": ms, "points": nvalid, "algorithmic_GBps": by / 1e9 / (ms / 1e3),
+                                              "frac_of_hbm_peak": by / 1e9 / (ms / 1e3) / load_peaks()[0]}
+        del metres, res_bp
+        ms = timed(lambda: ops.depth_from_u16(depth_u16, 1000.0, 3.0), 3)
+        extras["a4_depth_from_u16_GBps"] = 6 * F * H * W / 1e9 / (ms / 1e3)
+        t0 = time.perf_counter()
+        pcd = vol.extract_point_cloud()
+        torch.cuda.synchronize()
+        extras["points_ms"], extras["points"] = 1e3 * (time.perf_counter() - t0), int(pcd.points.shape[0])
+        del pcd
 
     # ---- CPU baseline (rank 0, N = 1): the oracle on a bounded sample of the same frames
     cpu = None
@@ -354,8 +433,12 @@ def main():
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        launches_per_step = 1 + 3 * ((F + (args.batch or 256) - 1) // (args.batch or 256))
-        ach = (bytes_algo_local * args.steps / 1e9) / (k_ms / 1e3) if k_ms > 0 else None
+        # a4 + per <=256-frame chunk: depth_stats, frame_soa, super_cull, brick_cull, brick_integrate
+        launches_per_step = 1 + 5 * ((F + (args.batch or 256) - 1) // (args.batch or 256))
+        # the library times up to 2048 integrate launches; use the whole steps it recorded
+        steps_timed = k_launches // len(chunks)
+        ach = (bytes_algo_local * steps_timed / 1e9) / (k_ms * (steps_timed * len(chunks) / k_launches) / 1e3) if k_ms > 0 and steps_timed else None
+        traffic, traffic_src = load_traffic(args, world, res, F)
         line = {
             "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -370,8 +453,8 @@ def main():
             "e2e": {"value": fps_e2e, "unit": UNIT, "h2d_bytes_per_step": F * H * W * 2 + F * 128, "d2h_bytes_per_step": F * 8},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "kernel": "brick_integrate_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
-                         "frac": (ach / peak) if ach else None, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_step": bytes_algo_local, "kernel_ms_per_step": k_ms / args.steps,
+                         "frac": (ach / peak) if ach else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "algorithmic_bytes_per_step": bytes_algo_local, "kernel_ms_per_step": k_ms / k_launches * len(chunks) if k_launches else None,
                          "kernel_launches": k_launches,
                          "note": "algorithmic bytes = 16 B x voxels updated per frame (oracle-equal count) + 4*W*H per frame; the kernel keeps "
                                  "a voxel in registers across the <=256 frames of a launch, so DRAM traffic is far below this figure"},

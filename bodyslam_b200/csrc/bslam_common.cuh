@@ -79,7 +79,8 @@ struct bslam_volume {
     // optional per-launch timing of the dominant kernel (bslam_tsdf_profile)
     int batch; // frames per integrate launch (0 = default)
     int prof_enabled, prof_n;
-    cudaEvent_t prof_ev[2 * 64];
+    static constexpr int kProfPairs = 2048;   // integrate launches timed per bslam_tsdf_profile_read
+    cudaEvent_t prof_ev[2 * kProfPairs];
     double prof_ms_accum;
     long long prof_launches_accum;
 };

@@ -8,6 +8,7 @@
 //   a4  N/3DM/slam_utils.py:212-220,231-233
 //   K2  N/3DM/scaling_system.py:72-77, N/3DM/mapping_module.py:37,41
 #include <math.h>
+#include <stdlib.h>
 
 #include "bslam_common.cuh"
 
@@ -135,61 +136,104 @@ __device__ double numpy_lerp(double a, double b, double t) {
 }
 
 // mode 0: percentile colorize table; mode 1: min-max uint8 table; mode 2: median only
+// grid = (images, kTableSlices): every CTA of an image recomputes the image's order statistics
+// from the 256 KB histogram (L2-resident; each thread keeps its 64 bins in registers) and then
+// builds only its own 1/kTableSlices of the 65 536-entry index table -- the 65 536 f64 divisions
+// per image are the long pole, so they are spread over kTableSlices SMs.
+constexpr int kTableSlices = 8;
+
 __global__ void __launch_bounds__(1024) stats_table_kernel(void *ws, double p_lo, double p_hi, const double *vmin_vmax_override /*device*/,
                                                            double *vmin_vmax_out, double *median_out, int mode,
                                                            const uint8_t *table_override) {
-    __shared__ unsigned long long s_part[1024];
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_before[4];
+    __shared__ int s_owner[4];
     __shared__ double s_vals[4];
     __shared__ unsigned int s_mm[2];
-    const int b = blockIdx.x, t = threadIdx.x;
+    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, wid = t >> 5;
+    const int slice = blockIdx.y, n_slices = gridDim.y;
+    const int i_begin = (int)((int64_t)kBins * slice / n_slices), i_end = (int)((int64_t)kBins * (slice + 1) / n_slices);
     const unsigned int *hist = ws_hist(ws, b);
     uint8_t *table = ws_table(ws, b);
     ImgStats *st = ws_stats(ws, b);
     if (table_override) { // value_transform path: the host supplies the table
-        for (int i = t; i < kBins; i += 1024) table[i] = table_override[(size_t)b * kBins + i];
+        for (int i = i_begin + t; i < i_end; i += 1024) table[i] = table_override[(size_t)b * kBins + i];
         return;
     }
-    constexpr int kPer = kBins / 1024; // 64 bins per thread
+    constexpr int kPer = kBins / 1024; // 64 consecutive bins per thread, fetched as 16-byte words
     unsigned long long local = 0;
     unsigned int lmin = 0xffffffffu, lmax = 0;
-    for (int i = 0; i < kPer; ++i) {
-        const unsigned int c = hist[t * kPer + i];
-        local += c;
-        if (c) { lmin = min(lmin, (unsigned int)(t * kPer + i)); lmax = max(lmax, (unsigned int)(t * kPer + i)); }
+#pragma unroll 4
+    for (int i = 0; i < kPer / 4; ++i) {
+        const uint4 c4 = reinterpret_cast<const uint4 *>(hist + t * kPer)[i];
+        const unsigned int c[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            local += c[j];
+            if (c[j]) { lmin = min(lmin, (unsigned int)(t * kPer + 4 * i + j)); lmax = max(lmax, (unsigned int)(t * kPer + 4 * i + j)); }
+        }
     }
-    s_part[t] = local;
     if (t == 0) { s_mm[0] = 0xffffffffu; s_mm[1] = 0; }
-    __syncthreads();
-    if (lmin != 0xffffffffu) { atomicMin(&s_mm[0], lmin); atomicMax(&s_mm[1], lmax); }
-    // inclusive scan of 1024 partials (Hillis-Steele; 10 steps)
-    for (int o = 1; o < 1024; o <<= 1) {
-        unsigned long long add = (t >= o) ? s_part[t - o] : 0ull;
-        __syncthreads();
-        s_part[t] += add;
-        __syncthreads();
+    // inclusive scan of the 1024 partial sums: warp shuffles, then the 32 warp totals
+    unsigned long long inc = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long up = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += up;
     }
-    const unsigned long long n = s_part[1023];
-    const unsigned long long before = s_part[t] - local; // exclusive prefix of this thread's bins
+    if (lane == 31) s_warp[wid] = inc;
+    __syncthreads();
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        lmin = min(lmin, __shfl_xor_sync(0xffffffffu, lmin, o));
+        lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+    }
+    if (lane == 0 && lmin != 0xffffffffu) { atomicMin(&s_mm[0], lmin); atomicMax(&s_mm[1], lmax); }
+    if (wid == 0) {
+        const unsigned long long w = s_warp[lane];
+        unsigned long long winc = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long up = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += up;
+        }
+        s_warp[lane] = winc;   // inclusive over warps
+    }
+    __syncthreads();
+    const unsigned long long n = s_warp[31];
+    const unsigned long long before = (wid ? s_warp[wid - 1] : 0ull) + inc - local; // exclusive prefix of this thread's bins
+    // wanted sorted positions: floor((n-1)*q) and +1 for both quantiles (and the medians).  The thread
+    // whose 64 bins hold a wanted position publishes itself; warp j then finds position j's bin with
+    // two coalesced loads per lane and a warp scan (a serial walk over the 64 bins costs 64 L2 round trips)
+    unsigned long long want[4] = {0, 0, 0, 0};
     if (n > 0) {
-        // wanted sorted positions: floor((n-1)*q) and +1 for both quantiles (and the medians)
         double q[2] = {p_lo / 100.0, p_hi / 100.0};
         if (mode == 2) { q[0] = 0.5; q[1] = 0.5; }
+#pragma unroll
         for (int k = 0; k < 2; ++k) {
             const double virt = (double)(n - 1) * q[k];
-            const double prev = floor(virt);
-            unsigned long long i0 = (unsigned long long)prev, i1 = i0 + 1;
-            if (i1 > n - 1) i1 = n - 1;
-            // does this thread's bin range hold sorted element i0 / i1 ?
-            unsigned long long acc = before;
-            for (int i = 0; i < kPer; ++i) {
-                const unsigned int c = hist[t * kPer + i];
-                if (c) {
-                    if (i0 >= acc && i0 < acc + c) s_vals[2 * k] = (double)(t * kPer + i);
-                    if (i1 >= acc && i1 < acc + c) s_vals[2 * k + 1] = (double)(t * kPer + i);
-                }
-                acc += c;
-            }
+            const unsigned long long i0 = (unsigned long long)floor(virt);
+            want[2 * k] = i0;
+            want[2 * k + 1] = (i0 + 1 > n - 1) ? n - 1 : i0 + 1;
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (want[j] >= before && want[j] < before + local) { s_owner[j] = t; s_before[j] = before; }
+    }
+    __syncthreads();
+    if (n > 0 && wid < 4) {
+        const int owner = s_owner[wid];
+        const unsigned long long rel = want[wid] - s_before[wid];      // 0 <= rel < the owner's 64-bin total
+        const unsigned int c0 = hist[owner * kPer + lane], c1 = hist[owner * kPer + 32 + lane];
+        unsigned long long a0 = c0, a1 = c1;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long u0 = __shfl_up_sync(0xffffffffu, a0, o), u1 = __shfl_up_sync(0xffffffffu, a1, o);
+            if (lane >= o) { a0 += u0; a1 += u1; }
+        }
+        a1 += __shfl_sync(0xffffffffu, a0, 31);
+        const unsigned int m0 = __ballot_sync(0xffffffffu, a0 > rel), m1 = __ballot_sync(0xffffffffu, a1 > rel);
+        if (lane == 0) s_vals[wid] = (double)(owner * kPer + (m0 ? __ffs(m0) - 1 : 32 + __ffs(m1) - 1));
     }
     __syncthreads();
     if (t == 0) {
@@ -197,9 +241,7 @@ __global__ void __launch_bounds__(1024) stats_table_kernel(void *ws, double p_lo
         if (n > 0) {
             if (mode == 2) {
                 // numpy median: mean of the two middle elements (they coincide for odd n)
-                const double virt = (double)(n - 1) * 0.5;
                 const bool odd = (n & 1ull) != 0;
-                (void)virt;
                 vmin = vmax = odd ? s_vals[0] : (s_vals[0] + s_vals[1]) / 2.0;
             } else {
                 const double v0 = (double)(n - 1) * (p_lo / 100.0), v1 = (double)(n - 1) * (p_hi / 100.0);
@@ -213,15 +255,17 @@ __global__ void __launch_bounds__(1024) stats_table_kernel(void *ws, double p_lo
             if (a == a) vmin = a;
             if (c == c) vmax = c;
         }
-        st->vmin = vmin; st->vmax = vmax; st->n_valid = n; st->vmin_u = s_mm[0]; st->vmax_u = s_mm[1];
-        if (vmin_vmax_out) { vmin_vmax_out[2 * b] = vmin; vmin_vmax_out[2 * b + 1] = vmax; }
-        if (median_out) median_out[b] = vmin;
+        if (slice == 0) {
+            st->vmin = vmin; st->vmax = vmax; st->n_valid = n; st->vmin_u = s_mm[0]; st->vmax_u = s_mm[1];
+            if (vmin_vmax_out) { vmin_vmax_out[2 * b] = vmin; vmin_vmax_out[2 * b + 1] = vmax; }
+            if (median_out) median_out[b] = vmin;
+        }
         s_vals[0] = vmin; s_vals[1] = vmax;
     }
     __syncthreads();
     if (mode == 2) return;
     const double vmin = s_vals[0], vmax = s_vals[1];
-    for (int i = t; i < kBins; i += 1024) {
+    for (int i = i_begin + t; i < i_end; i += 1024) {
         unsigned int idx;
         if (mode == 0) {
             // colorize: x = (value - vmin)/(vmax - vmin) (f64), matplotlib: trunc(x*256) with
@@ -320,22 +364,147 @@ __global__ void depth_from_u16_kernel(const uint16_t *__restrict__ in, int64_t n
 }
 
 // ---------------------------------------------------------------- K2: back-projection + SE(3)
-constexpr int kBpMaxImages = 64;   // poses per launch, passed by value -> constant bank
+// Order-preserving compaction in three launches, none of which has a cross-CTA dependency:
+//   bp_count_kernel : streams the depth once; a warp owns "warp tiles" of 256 visited pixels and
+//                     writes each tile's valid count as an offset inside its CTA (32 tiles) plus
+//                     the CTA total.
+//   bp_scan_kernel  : one CTA turns the CTA totals into i64 bases and the per-image row counts.
+//   bp_emit_kernel  : streams the depth again; every warp works alone (no block barrier): ballots
+//                     rank its tile's valid pixels in row-major order, points are staged in the
+//                     warp's 3 KB of shared memory and leave as fully coalesced 4-byte words.
+// (A single-pass decoupled look-back version was measured first: its CTAs spend their life in four
+//  barrier-separated global round trips -- ticket, depth, look-back, write -- and reached 1.1 TB/s.)
+constexpr int kBpMaxImages = 64;       // poses per emit launch, passed by value -> constant bank
 constexpr int kBpThreads = 256;
-constexpr int kBpPerThread = 4;
-constexpr int kBpPerBlock = kBpThreads * kBpPerThread;
+constexpr int kBpWarps = kBpThreads / 32;
+constexpr int kBpTilePx = 256;         // visited pixels per warp tile (8 per lane)
+constexpr int kBpTilesPerWarp = 4;
+constexpr int kBpTilesPerCta = kBpWarps * kBpTilesPerWarp;   // 32
 
 struct BackprojP {
-    float fx, fy, cx, cy;
+    float fx, fy, cx, cy, inv_fx, inv_fy;
     int H, W, Hs, Ws, stride;
-    int blocks_per_image;
+    int tiles_per_image, ctas_per_image;
+    int img0, n_images;      // images of this launch (poses below are for img0 .. img0 + n_images - 1)
     float pose[kBpMaxImages][12];
 };
 
+struct BackprojWs {
+    int *tile_off;           // [B * ctas_per_image * 32] exclusive offset of a tile inside its CTA
+    int *cta_total;          // [B * ctas_per_image]
+    long long *cta_base;     // [B * ctas_per_image] exclusive prefix over all CTAs (row index of the CTA's first point)
+};
+
+// visited pixel q of the strided grid -> (row v, column u) of the image: float estimate + exact correction
+__device__ __forceinline__ void bp_pixel(const BackprojP &bp, float inv_ws, unsigned int q, int &u, int &v) {
+    int r = (int)((float)q * inv_ws);
+    int c = (int)q - r * bp.Ws;
+    r += (c >= bp.Ws) - (c < 0);
+    c = (int)q - r * bp.Ws;
+    v = r * bp.stride; u = c * bp.stride;
+}
+
+__global__ void __launch_bounds__(kBpThreads) bp_count_kernel(const __grid_constant__ BackprojP bp, const float *__restrict__ depth, int valid_only,
+                                                              BackprojWs ws) {
+    __shared__ int s_cnt[kBpTilesPerCta];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned int img = blockIdx.x / (unsigned int)bp.ctas_per_image;
+    const unsigned int cta_in_img = blockIdx.x - img * (unsigned int)bp.ctas_per_image;
+    const unsigned int n_vis = (unsigned int)(bp.Hs * bp.Ws);
+    const float *dimg = depth + (int64_t)img * bp.H * bp.W;
+    const float inv_ws = 1.0f / (float)bp.Ws;
+    const bool vec = (bp.stride == 1) && ((reinterpret_cast<uintptr_t>(dimg) & 15) == 0);
+    int cnt[kBpTilesPerWarp];
+#pragma unroll
+    for (int t = 0; t < kBpTilesPerWarp; ++t) {
+        const unsigned int tile = cta_in_img * kBpTilesPerCta + wid * kBpTilesPerWarp + t;
+        const unsigned int q0 = tile * kBpTilePx;
+        int c = 0;
+        if (vec && q0 + kBpTilePx <= n_vis) {            // whole tile, contiguous pixels: two 16-byte loads per lane
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(dimg + q0) + lane);
+            const float4 b = __ldg(reinterpret_cast<const float4 *>(dimg + q0) + 32 + lane);
+            c = (a.x > 0.f) + (a.y > 0.f) + (a.z > 0.f) + (a.w > 0.f) + (b.x > 0.f) + (b.y > 0.f) + (b.z > 0.f) + (b.w > 0.f);
+            if (!valid_only) c = 8;
+        } else {
+#pragma unroll
+            for (int j = 0; j < kBpTilePx / 32; ++j) {
+                const unsigned int q = q0 + j * 32 + lane;
+                if (q < n_vis) {
+                    int u, v;
+                    bp_pixel(bp, inv_ws, q, u, v);
+                    c += valid_only ? (__ldg(dimg + v * bp.W + u) > 0.f) : 1;
+                }
+            }
+        }
+        cnt[t] = __reduce_add_sync(0xffffffffu, c);
+    }
+    if (lane == 0) {
+#pragma unroll
+        for (int t = 0; t < kBpTilesPerWarp; ++t) s_cnt[wid * kBpTilesPerWarp + t] = cnt[t];
+    }
+    __syncthreads();
+    if (wid == 0) {
+        const int c = s_cnt[lane];
+        int inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        ws.tile_off[(size_t)blockIdx.x * kBpTilesPerCta + lane] = inc - c;
+        if (lane == 31) ws.cta_total[blockIdx.x] = inc;
+    }
+}
+
+// exclusive i64 scan of the CTA totals (one CTA; n is a few thousand) + per-image row counts
+__global__ void __launch_bounds__(1024) bp_scan_kernel(BackprojWs ws, int n_ctas, int ctas_per_image, int B, long long *counts /*[B+1]*/) {
+    __shared__ long long s_warp[32];
+    __shared__ long long s_carry;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_ctas; base += 1024) {
+        const int i = base + threadIdx.x;
+        const long long c = (i < n_ctas) ? ws.cta_total[i] : 0;
+        long long inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const long long t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            const long long w = s_warp[lane];
+            long long winc = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const long long t = __shfl_up_sync(0xffffffffu, winc, o);
+                if (lane >= o) winc += t;
+            }
+            s_warp[lane] = winc - w;     // exclusive over warps
+        }
+        __syncthreads();
+        const long long carry = s_carry;
+        if (i < n_ctas) ws.cta_base[i] = carry + s_warp[wid] + inc - c;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + s_warp[31] + inc;
+        __syncthreads();
+    }
+    // rows of image k = base of the first CTA of image k+1 (or the grand total) - base of its own first CTA
+    for (int k = threadIdx.x; k < B; k += 1024) {
+        const long long lo = ws.cta_base[(size_t)k * ctas_per_image];
+        const long long hi = (k + 1 < B) ? ws.cta_base[(size_t)(k + 1) * ctas_per_image] : s_carry;
+        counts[k] = hi - lo;
+    }
+    if (threadIdx.x == 0) counts[B] = s_carry;
+}
+
 __device__ __forceinline__ float3 backproject_px(const BackprojP &bp, int img, int u, int v, float d) {
     // pixel_to_3d (scaling_system.py:72-77): x = (u - cx) * depth / fx ; then the rigid transform
-    const float x = ((float)u - bp.cx) * d / bp.fx;
-    const float y = ((float)v - bp.cy) * d / bp.fy;
+    // (f32; the f64 reference value is matched to ~2 ulp either way: reciprocal multiply instead of two IEEE divisions)
+    const float x = ((float)u - bp.cx) * d * bp.inv_fx;
+    const float y = ((float)v - bp.cy) * d * bp.inv_fy;
     const float *M = bp.pose[img];
     float3 p;
     p.x = fmaf(M[0], x, fmaf(M[1], y, fmaf(M[2], d, M[3])));
@@ -344,102 +513,77 @@ __device__ __forceinline__ float3 backproject_px(const BackprojP &bp, int img, i
     return p;
 }
 
-// PHASE 0: per-block valid counts; PHASE 1: emit (offsets = exclusive scan of the counts)
-template <int PHASE>
-__global__ void __launch_bounds__(kBpThreads) backproject_kernel(const __grid_constant__ BackprojP bp, const float *__restrict__ depth,
-                                                                  const uint8_t *__restrict__ rgb_u8, int img0, int valid_only,
-                                                                  float *__restrict__ xyz, float *__restrict__ rgb, int64_t capacity,
-                                                                  long long *__restrict__ block_counts, const long long *__restrict__ block_offsets) {
-    __shared__ int s_warp[kBpThreads / 32];
-    const int img = blockIdx.y;
-    const int64_t n_vis = (int64_t)bp.Hs * bp.Ws;
-    const int64_t first = (int64_t)blockIdx.x * kBpPerBlock + threadIdx.x * kBpPerThread;
-    const float *dimg = depth + (int64_t)(img0 + img) * bp.H * bp.W;
-    float d[kBpPerThread]; int uu[kBpPerThread], vv[kBpPerThread];
-    int cnt = 0;
-#pragma unroll
-    for (int j = 0; j < kBpPerThread; ++j) {
-        const int64_t q = first + j;
-        d[j] = -1.0f;
-        if (q < n_vis) {
-            const int r = (int)(q / bp.Ws), c = (int)(q % bp.Ws);
-            vv[j] = r * bp.stride; uu[j] = c * bp.stride;
-            d[j] = __ldg(dimg + (int64_t)vv[j] * bp.W + uu[j]);
-            if (!(d[j] > 0.0f)) d[j] = 0.0f; // invalid but visited
-            cnt += (d[j] > 0.0f) || !valid_only;
-        }
-    }
-    // block exclusive scan of cnt
+template <bool WITH_RGB>
+__global__ void __launch_bounds__(kBpThreads) bp_emit_kernel(const __grid_constant__ BackprojP bp, const float *__restrict__ depth,
+                                                             const uint8_t *__restrict__ rgb_u8, int valid_only,
+                                                             float *__restrict__ xyz, float *__restrict__ rgb, int64_t capacity,
+                                                             BackprojWs ws) {
+    __shared__ float s_xyz[kBpWarps][kBpTilePx * 3];
+    __shared__ float s_rgb[WITH_RGB ? kBpWarps : 1][WITH_RGB ? kBpTilePx * 3 : 1];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    int inc = cnt;
-    for (int o = 1; o < 32; o <<= 1) {
-        const int t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) s_warp[wid] = inc;
-    __syncthreads();
-    int wbase = 0, total = 0;
-    for (int w = 0; w < kBpThreads / 32; ++w) {
-        if (w < wid) wbase += s_warp[w];
-        total += s_warp[w];
-    }
-    const int64_t gblock = (int64_t)img * bp.blocks_per_image + blockIdx.x;
-    if (PHASE == 0) {
-        if (threadIdx.x == 0) block_counts[gblock] = total;
-        return;
-    }
-    int64_t o = block_offsets[gblock] + wbase + inc - cnt;
+    const unsigned int gcta = (unsigned int)bp.img0 * bp.ctas_per_image + blockIdx.x;   // CTA index of the count pass
+    const unsigned int img = gcta / (unsigned int)bp.ctas_per_image;
+    const unsigned int cta_in_img = gcta - img * (unsigned int)bp.ctas_per_image;
+    const int img_local = (int)img - bp.img0;
+    const unsigned int n_vis = (unsigned int)(bp.Hs * bp.Ws);
+    const float *dimg = depth + (int64_t)img * bp.H * bp.W;
+    const float inv_ws = 1.0f / (float)bp.Ws;
+    const long long cta_base = ws.cta_base[gcta];
+    float *sx = s_xyz[wid], *sc = s_rgb[WITH_RGB ? wid : 0];
+#pragma unroll 1
+    for (int t = 0; t < kBpTilesPerWarp; ++t) {
+        const unsigned int tile_in_cta = wid * kBpTilesPerWarp + t;
+        const unsigned int q0 = (cta_in_img * kBpTilesPerCta + tile_in_cta) * kBpTilePx;
+        if (q0 >= n_vis) break;
+        const long long base = cta_base + ws.tile_off[(size_t)gcta * kBpTilesPerCta + tile_in_cta];
+        // addresses, then all eight loads back to back, then the ballots (a ballot is a convergence
+        // point: fused into one loop the loads would be issued one DRAM round trip after the other)
+        int off[kBpTilePx / 32];
+        unsigned int uv[kBpTilePx / 32];
+        float d[kBpTilePx / 32];
 #pragma unroll
-    for (int j = 0; j < kBpPerThread; ++j) {
-        if (d[j] < 0.0f) continue;
-        const bool valid = d[j] > 0.0f;
-        if (!valid && valid_only) continue;
-        if (o < capacity) {
-            float3 p = make_float3(NAN, NAN, NAN);
-            if (valid) p = backproject_px(bp, img, uu[j], vv[j], d[j]);
-            xyz[3 * o + 0] = p.x; xyz[3 * o + 1] = p.y; xyz[3 * o + 2] = p.z;
-            if (rgb && rgb_u8) {
-                const uint8_t *c = rgb_u8 + ((int64_t)(img0 + img) * bp.H * bp.W + (int64_t)vv[j] * bp.W + uu[j]) * 3;
-                rgb[3 * o + 0] = valid ? c[0] / 255.0f : NAN;
-                rgb[3 * o + 1] = valid ? c[1] / 255.0f : NAN;
-                rgb[3 * o + 2] = valid ? c[2] / 255.0f : NAN;
+        for (int j = 0; j < kBpTilePx / 32; ++j) {
+            const unsigned int q = q0 + j * 32 + lane;     // lane-consecutive pixels
+            int u, v;
+            bp_pixel(bp, inv_ws, q, u, v);
+            uv[j] = ((unsigned int)v << 16) | (unsigned int)u;
+            off[j] = (q < n_vis) ? v * bp.W + u : -1;
+        }
+#pragma unroll
+        for (int j = 0; j < kBpTilePx / 32; ++j) d[j] = (off[j] >= 0) ? __ldg(dimg + off[j]) : -1.0f;   // -1: not visited
+        int n = 0;                                           // points staged so far (warp-uniform)
+#pragma unroll
+        for (int j = 0; j < kBpTilePx / 32; ++j) {
+            const bool visited = off[j] >= 0;
+            const bool valid = d[j] > 0.0f;
+            const bool emit = visited && (valid || !valid_only);
+            const unsigned int bal = __ballot_sync(0xffffffffu, emit);
+            if (emit) {
+                const int o = n + __popc(bal & ((1u << lane) - 1u));
+                const int v = (int)(uv[j] >> 16), u = (int)(uv[j] & 0xffffu);
+                float3 p = make_float3(NAN, NAN, NAN);
+                if (valid) p = backproject_px(bp, img_local, u, v, d[j]);
+                sx[3 * o + 0] = p.x; sx[3 * o + 1] = p.y; sx[3 * o + 2] = p.z;
+                if (WITH_RGB) {
+                    const uint8_t *c = rgb_u8 + ((int64_t)img * bp.H * bp.W + off[j]) * 3;
+                    sc[3 * o + 0] = valid ? c[0] / 255.0f : NAN;
+                    sc[3 * o + 1] = valid ? c[1] / 255.0f : NAN;
+                    sc[3 * o + 2] = valid ? c[2] / 255.0f : NAN;
+                }
             }
+            n += __popc(bal);
         }
-        ++o;
-    }
-}
-
-// exclusive scan of `n` block counts with a carried-in base; also writes per-image totals
-__global__ void __launch_bounds__(1024) scan_counts_kernel(const long long *counts, long long *offsets, int64_t n, int blocks_per_image,
-                                                           int n_images, long long *image_counts /*[n_images]*/, long long *running_total /*[1]*/) {
-    __shared__ long long s[1024];
-    __shared__ long long s_carry;
-    if (threadIdx.x == 0) s_carry = *running_total;
-    __syncthreads();
-    for (int64_t base = 0; base < n; base += 1024) {
-        const int64_t i = base + threadIdx.x;
-        const long long c = (i < n) ? counts[i] : 0;
-        s[threadIdx.x] = c;
-        __syncthreads();
-        for (int o = 1; o < 1024; o <<= 1) {
-            const long long add = (threadIdx.x >= o) ? s[threadIdx.x - o] : 0;
-            __syncthreads();
-            s[threadIdx.x] += add;
-            __syncthreads();
+        __syncwarp();
+        const long long room = capacity - base;
+        const int n_write = (int)max(0ll, min((long long)n, room));
+        float *dst = xyz + 3 * base;
+        for (int i = lane; i < 3 * n_write; i += 32) dst[i] = sx[i];
+        if (WITH_RGB) {
+            float *dstc = rgb + 3 * base;
+            for (int i = lane; i < 3 * n_write; i += 32) dstc[i] = sc[i];
         }
-        if (i < n) offsets[i] = s_carry + s[threadIdx.x] - c;
-        __syncthreads();
-        if (threadIdx.x == 1023) s_carry += s[1023];
-        __syncthreads();
+        __syncwarp();
     }
-    // per-image totals from the offsets (image k spans blocks [k*bpi, (k+1)*bpi))
-    for (int k = threadIdx.x; k < n_images; k += 1024) {
-        const long long lo = offsets[(int64_t)k * blocks_per_image];
-        const long long hi = (k + 1 < n_images) ? offsets[(int64_t)(k + 1) * blocks_per_image] : s_carry;
-        image_counts[k] = hi - lo;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) *running_total = s_carry;
 }
 
 static int grid_for(int64_t work_items, int per_block) {
@@ -495,7 +639,7 @@ int bslam_colorize(const float *d_depth_m, const uint16_t *d_u16_in, int B, int 
         d_override = (double *)((char *)d_workspace + (size_t)B * kWsPerImage);
         BSLAM_CUDA(cudaMemcpyAsync(d_override, h_vmin_vmax, (size_t)B * 16, cudaMemcpyHostToDevice, st));
     }
-    stats_table_kernel<<<B, 1024, 0, st>>>(d_workspace, p_lo, p_hi, d_override, d_vmin_vmax_out, nullptr, 0, d_table_override);
+    stats_table_kernel<<<dim3((unsigned)B, kTableSlices), 1024, 0, st>>>(d_workspace, p_lo, p_hi, d_override, d_vmin_vmax_out, nullptr, 0, d_table_override);
     BSLAM_LAUNCH_CHECK();
     const uint16_t *src = d_depth_m ? d_u16_out : d_u16_in;
     const dim3 grid((unsigned)grid_for(n, 1024 * 4), (unsigned)B);
@@ -513,7 +657,7 @@ int bslam_minmax_u8(const uint16_t *d_u16, int B, int H, int W, uint8_t *d_gray,
     const int64_t n = (int64_t)H * W;
     int rc = run_hist(nullptr, d_u16, B, n, 1.0f, nullptr, 0, 0, d_workspace, st);
     if (rc) return rc;
-    stats_table_kernel<<<B, 1024, 0, st>>>(d_workspace, 0, 100, nullptr, nullptr, nullptr, 1, nullptr);
+    stats_table_kernel<<<dim3((unsigned)B, kTableSlices), 1024, 0, st>>>(d_workspace, 0, 100, nullptr, nullptr, nullptr, 1, nullptr);
     BSLAM_LAUNCH_CHECK();
     const dim3 grid((unsigned)grid_for(n, 1024 * 4), (unsigned)B);
     apply_table_kernel<3><<<grid, 256, 0, st>>>(d_u16, n, d_lut3, 0, 0, 0, d_rgb, d_gray, d_workspace);
@@ -527,7 +671,7 @@ int bslam_median_u16(const uint16_t *d_u16, int B, int64_t n_per_image, int has_
     cudaStream_t st = (cudaStream_t)stream;
     int rc = run_hist(nullptr, d_u16, B, n_per_image, 1.0f, nullptr, has_invalid, invalid_val, d_workspace, st);
     if (rc) return rc;
-    stats_table_kernel<<<B, 1024, 0, st>>>(d_workspace, 50, 50, nullptr, nullptr, d_out, 2, nullptr);
+    stats_table_kernel<<<dim3((unsigned)B, 1), 1024, 0, st>>>(d_workspace, 50, 50, nullptr, nullptr, d_out, 2, nullptr);
     BSLAM_LAUNCH_CHECK();
     return BSLAM_OK;
 }
@@ -541,14 +685,16 @@ int bslam_depth_from_u16(const uint16_t *d_in, int64_t n, float depth_scale, flo
     return BSLAM_OK;
 }
 
-static int bp_blocks_per_image(int H, int W, int stride) {
+static int bp_tiles_per_image(int H, int W, int stride) {
     const int64_t n_vis = (int64_t)((H + stride - 1) / stride) * ((W + stride - 1) / stride);
-    return (int)((n_vis + kBpPerBlock - 1) / kBpPerBlock);
+    return (int)((n_vis + kBpTilePx - 1) / kBpTilePx);
 }
+static int bp_ctas_per_image(int H, int W, int stride) { return (bp_tiles_per_image(H, W, stride) + kBpTilesPerCta - 1) / kBpTilesPerCta; }
 
 size_t bslam_backproject_workspace_bytes(int B, int H, int W, int stride) {
     if (B <= 0 || H <= 0 || W <= 0 || stride <= 0) return 0;
-    return (size_t)B * bp_blocks_per_image(H, W, stride) * 16 + 256;
+    const size_t n_ctas = (size_t)B * bp_ctas_per_image(H, W, stride);
+    return n_ctas * kBpTilesPerCta * 4 + n_ctas * 4 + n_ctas * 8 + 3 * 256;
 }
 
 int bslam_backproject(const float *d_depth, const uint8_t *d_rgb_u8, int B, int H, int W, int stride, const float *h_K,
@@ -557,30 +703,36 @@ int bslam_backproject(const float *d_depth, const uint8_t *d_rgb_u8, int B, int 
     BSLAM_CHECK_ARG(d_depth && h_K && h_cam_to_world && d_xyz && d_counts && d_workspace, "bslam_backproject: NULL argument");
     BSLAM_CHECK_ARG(B > 0 && H > 0 && W > 0 && stride > 0, "bslam_backproject: bad shape");
     BSLAM_CHECK_ARG(!(d_rgb && !d_rgb_u8), "bslam_backproject: colour output needs the RGB8 image");
+    BSLAM_CHECK_ARG(H <= 65535 && W <= 65535 && (int64_t)H * W < (1ll << 31), "bslam_backproject: image too large");
     cudaStream_t st = (cudaStream_t)stream;
     static thread_local BackprojP bp;
     bp.fx = h_K[0]; bp.fy = h_K[1]; bp.cx = h_K[2]; bp.cy = h_K[3];
+    bp.inv_fx = (float)(1.0 / (double)h_K[0]); bp.inv_fy = (float)(1.0 / (double)h_K[1]);
     bp.H = H; bp.W = W; bp.stride = stride;
     bp.Hs = (H + stride - 1) / stride; bp.Ws = (W + stride - 1) / stride;
-    bp.blocks_per_image = bp_blocks_per_image(H, W, stride);
-    long long *counts = (long long *)((char *)d_workspace + 256);
-    long long *offsets = counts + (size_t)B * bp.blocks_per_image;
-    long long *running = (long long *)d_workspace;
-    BSLAM_CUDA(cudaMemsetAsync(running, 0, 8, st));
+    bp.tiles_per_image = bp_tiles_per_image(H, W, stride);
+    bp.ctas_per_image = bp_ctas_per_image(H, W, stride);
+    const int64_t n_ctas = (int64_t)B * bp.ctas_per_image;
+    BSLAM_CHECK_ARG(n_ctas < (1ll << 31), "bslam_backproject: too many tiles");
+    BackprojWs ws;
+    char *w = (char *)d_workspace;
+    ws.cta_base = (long long *)w;  w += ((size_t)n_ctas * 8 + 255) / 256 * 256;
+    ws.tile_off = (int *)w;        w += ((size_t)n_ctas * kBpTilesPerCta * 4 + 255) / 256 * 256;
+    ws.cta_total = (int *)w;
+    bp.img0 = 0; bp.n_images = B;
+    bp_count_kernel<<<(unsigned)n_ctas, kBpThreads, 0, st>>>(bp, d_depth, valid_only, ws);
+    BSLAM_LAUNCH_CHECK();
+    bp_scan_kernel<<<1, 1024, 0, st>>>(ws, (int)n_ctas, bp.ctas_per_image, B, (long long *)d_counts);
+    BSLAM_LAUNCH_CHECK();
     for (int i0 = 0; i0 < B; i0 += kBpMaxImages) {
         const int nb = (B - i0 < kBpMaxImages) ? B - i0 : kBpMaxImages;
+        bp.img0 = i0; bp.n_images = nb;
         memcpy(bp.pose, h_cam_to_world + (size_t)i0 * 12, (size_t)nb * 12 * sizeof(float));
-        const dim3 grid((unsigned)bp.blocks_per_image, (unsigned)nb);
-        long long *c = counts + (size_t)i0 * bp.blocks_per_image, *o = offsets + (size_t)i0 * bp.blocks_per_image;
-        backproject_kernel<0><<<grid, kBpThreads, 0, st>>>(bp, d_depth, d_rgb_u8, i0, valid_only, d_xyz, d_rgb, capacity, c, o);
-        BSLAM_LAUNCH_CHECK();
-        scan_counts_kernel<<<1, 1024, 0, st>>>(c, o, (int64_t)nb * bp.blocks_per_image, bp.blocks_per_image, nb,
-                                                (long long *)d_counts + i0, running);
-        BSLAM_LAUNCH_CHECK();
-        backproject_kernel<1><<<grid, kBpThreads, 0, st>>>(bp, d_depth, d_rgb_u8, i0, valid_only, d_xyz, d_rgb, capacity, c, o);
+        const unsigned grid = (unsigned)(nb * bp.ctas_per_image);
+        if (d_rgb && d_rgb_u8) bp_emit_kernel<true><<<grid, kBpThreads, 0, st>>>(bp, d_depth, d_rgb_u8, valid_only, d_xyz, d_rgb, capacity, ws);
+        else bp_emit_kernel<false><<<grid, kBpThreads, 0, st>>>(bp, d_depth, nullptr, valid_only, d_xyz, nullptr, capacity, ws);
         BSLAM_LAUNCH_CHECK();
     }
-    BSLAM_CUDA(cudaMemcpyAsync((long long *)d_counts + B, running, 8, cudaMemcpyDeviceToDevice, st));
     return BSLAM_OK;
 }
 
