@@ -212,7 +212,7 @@ def main():
     from bodyslam_b200 import _lib, ops
     from bodyslam_b200 import synthetic as S
     from bodyslam_b200.geometry import PinholeCameraIntrinsic
-    from bodyslam_b200.sharding import slab_bounds
+    from bodyslam_b200.sharding import ShardedTSDF
     from bodyslam_b200.tsdf import DenseTSDFVolume
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -235,39 +235,20 @@ def main():
         depth_u16 = torch.empty((F, H, W), dtype=torch.uint16, device=dev)
     E_dev = torch.as_tensor(E, device=dev).contiguous()
     # N > 1: round-robin brick layers (rank r owns every N-th 8-voxel layer) -> balanced whatever the view
-    interleaved = world > 1 and (res // 8) % world == 0
-    if interleaved:
-        vol = DenseTSDFVolume(vl, trunc, (res, res, res // world), cfg["origin"], color=False, device=dev, gz0=8 * rank, z_total=res,
-                              z_interleave=world)
-    else:
-        z0, z1 = slab_bounds(res, world)[rank]
-        vol = DenseTSDFVolume(vl, trunc, (res, res, z1 - z0), cfg["origin"], color=False, device=dev, gz0=z0, z_total=res)
+    sh = ShardedTSDF(vl, trunc, res, cfg["origin"], color=False, device=dev, rank=rank, world_size=world)
+    vol = sh.tsdf
+    interleaved = sh.layout == "interleaved"
     if args.batch:
         vol.set_batch(args.batch)
-    depth_f = torch.empty((F, H, W), dtype=torch.float32, device=dev)
-    L = _lib.load()
-
-    def a4(src_u16, dst_f32):
-        _lib.check(L.bslam_depth_from_u16(_lib.ptr(src_u16), src_u16.numel(), 1000.0, 3.0, _lib.ptr(dst_f32), _lib.stream_ptr(dev)))
-
     chunk = args.batch or 256
-    chunks = [(f0, min(F, f0 + chunk)) for f0 in range(0, F, chunk)]
+    chunks = vol.stream_chunks(F, chunk, ramp=ShardedTSDF.stream_ramp(world, True))   # integrate launches of a resident step
 
     def step(src_u16, counts=None):
-        if world == 1:
-            a4(src_u16, depth_f)
-            vol.integrate_batch(depth_f, None, intr, E, update_counts=counts)
-            return
-        # rank 0 holds the frames: broadcast chunk k+1 over NCCL while chunk k is integrated
-        dist.broadcast(E_dev, 0)
-        u8 = src_u16.view(torch.uint8)  # NCCL has no 16-bit integer type: ship the bytes
-        work = dist.broadcast(u8[chunks[0][0]:chunks[0][1]], 0, async_op=True)
-        for k, (f0, f1) in enumerate(chunks):
-            work.wait()
-            if k + 1 < len(chunks):
-                work = dist.broadcast(u8[chunks[k + 1][0]:chunks[k + 1][1]], 0, async_op=True)
-            a4(src_u16[f0:f1], depth_f[f0:f1])
-            vol.integrate_batch(depth_f[f0:f1], None, intr, E[f0:f1], update_counts=None if counts is None else counts[f0:f1])
+        """one pass of the hot path over the whole trajectory through the public API: src_u16 is rank 0's
+        uint16 depth (device-resident for `value`, pinned host memory for `e2e`).  a4 is fused into the
+        integration's first pass; N > 1: rank 0's frames are broadcast over NCCL chunk by chunk, the
+        broadcast of chunk k+1 (and the H2D of chunk k+2) overlapping the integration of chunk k."""
+        sh.integrate_stream(src_u16, intr, E, src=0, depth_scale=1000.0, depth_trunc=3.0, chunk=chunk, update_counts=counts)
 
     def barrier():
         if world > 1:
@@ -284,8 +265,10 @@ def main():
     # ---- algorithmic bytes: U_f = voxels each frame updates (dry run, untimed), summed over slabs
     if world > 1:
         dist.broadcast(depth_u16.view(torch.uint8), 0)
-    a4(depth_u16, depth_f)
+    depth_f = ops.depth_from_u16(depth_u16, 1000.0, 3.0, dev)
+    vol.dry_stats(True)
     uf_local = vol.count_updates(depth_f, intr, E)
+    cull = vol.dry_stats(True)
     uf = uf_local.clone()
     if world > 1:
         dist.all_reduce(uf)
@@ -322,17 +305,12 @@ def main():
     if rank == 0:
         host_u16.copy_(depth_u16)
     counts = torch.zeros(F, dtype=torch.int64, device=dev)
-    stage_u16 = torch.empty_like(depth_u16) if world > 1 else None
 
     def e2e_step():
+        # public API: pinned host frames in (rank 0), per-frame update counts out; H2D, broadcast and
+        # integration are pipelined chunk by chunk inside integrate_stream
         counts.zero_()
-        if world == 1:
-            # public API: pinned host frames in, per-frame update counts out (H2D overlapped with compute)
-            vol.integrate_host(host_u16, None, intr, E, depth_scale=1000.0, depth_trunc=3.0, update_counts=counts)
-        else:
-            if rank == 0:
-                stage_u16.copy_(host_u16, non_blocking=True)
-            step(stage_u16, counts)
+        step(host_u16, counts)
         host_counts.copy_(counts, non_blocking=True)
 
     e2e_step()
@@ -433,8 +411,8 @@ def main():
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        # a4 + per <=256-frame chunk: depth_stats, frame_soa, super_cull, brick_cull, brick_integrate
-        launches_per_step = 1 + 5 * ((F + (args.batch or 256) - 1) // (args.batch or 256))
+        # per <=256-frame chunk: depth_stats (+ fused a4), frame_soa, super_cull, brick_cull, brick_integrate
+        launches_per_step = 5 * len(chunks)
         # the library times up to 2048 integrate launches; use the whole steps it recorded
         steps_timed = k_launches // len(chunks)
         ach = (bytes_algo_local * steps_timed / 1e9) / (k_ms * (steps_timed * len(chunks) / k_launches) / 1e3) if k_ms > 0 and steps_timed else None
@@ -445,7 +423,8 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"{WORKLOAD}: {F}-frame synthetic laparoscopy sweep, {W}x{H} u16 depth -> {res}^3 TSDF @ {vl * 1e3:g} mm, "
                                    f"sdf_trunc {trunc * 1e3:g} mm (BASELINE configs[3])",
-                       "frames_per_step": F, "step": "a4 depth scaling + K3 integrate of all frames, volume resident",
+                       "frames_per_step": F, "step": "a4 depth scaling (fused into the first pass) + K3 integrate of all frames, volume resident",
+                       "culling": {"voxels_tested_per_frame": cull["voxels_tested"] / F, "updated_over_tested": (int(uf_local.sum().item()) / cull["voxels_tested"]) if cull["voxels_tested"] else None},
                        "l2": "inputs larger than L2 (1.2 GB depth + 1.1 GB volume per step vs 126 MB)",
                        "parallelism": (f"round-robin brick-layer z-shards x{world}" if interleaved else f"z-slab x{world}") if world > 1 else "single GPU",
                        "voxels_updated_per_frame": uf_total / F, **extras},

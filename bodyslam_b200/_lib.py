@@ -35,9 +35,11 @@ _SIGNATURES = {
     "bslam_tsdf_reset": (C.c_int, [_p, _p]),
     "bslam_tsdf_copy": (C.c_int, [_p, _p, _p]),
     "bslam_tsdf_integrate": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_int, _p, _p, C.c_int, _p, C.c_int, _p]),
+    "bslam_tsdf_integrate_u16": (C.c_int, [_p, _p, C.c_float, C.c_float, _p, _p, C.c_int, C.c_int, C.c_int, _p, _p, _p, _p]),
     "bslam_tsdf_set_z_interleave": (C.c_int, [_p, C.c_int]),
     "bslam_tsdf_layout": (C.c_int, [_p, _p]),
     "bslam_tsdf_set_batch": (C.c_int, [_p, C.c_int]),
+    "bslam_tsdf_dry_stats": (C.c_int, [_p, _p, C.c_int, _p]),
     "bslam_selftest": (C.c_int, [C.c_ulonglong, C.c_uint, _p, _p]),
     "bslam_tsdf_profile": (C.c_int, [_p, C.c_int]),
     "bslam_tsdf_profile_read": (C.c_int, [_p, _p, _p]),

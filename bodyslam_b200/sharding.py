@@ -255,6 +255,99 @@ class ShardedTSDF:
             extrinsics = E.cpu().numpy()
         self.tsdf.integrate_batch(depth, color, intrinsic, extrinsics)
 
+    @staticmethod
+    def stream_ramp(world_size: int, src_on_device: bool):
+        """chunk ramp of a streamed replay: host frames arrive at PCIe speed, so start with 32 frames;
+        device-resident frames only have to cross NVLink (one 64-frame chunk hides the first
+        broadcast); a single GPU with resident frames has nothing to overlap."""
+        if world_size == 1 and src_on_device:
+            return ()
+        return (64,) if src_on_device else (32, 64, 128)
+
+    def integrate_stream(self, depth_u16, intrinsic, extrinsics, src: int = 0, depth_scale: float = 1000.0, depth_trunc: float = 3.0,
+                         chunk: int = 256, update_counts=None):
+        """Streamed replay of F uint16 frames held by rank `src` (host memory -- ideally pinned -- or
+        device memory) into every rank's shard.  Three stages overlap chunk by chunk:
+            rank src: host -> device copy of chunk k+2 (copy stream)
+            all     : NCCL broadcast of chunk k+1 over NVLink (NCCL's stream)
+            all     : fused depth conversion + integration of chunk k (current stream)
+        Every rank calls this with the same shapes; only `src` needs the data (`depth_u16` may be
+        None elsewhere if `shape` = (F, H, W) is given through `extrinsics`' length and intrinsic).
+        Integration itself has no data-path collective."""
+        import torch
+        import torch.distributed as dist
+
+        from .geometry import intrinsic_params, to_numpy
+
+        vol = self.tsdf
+        dev = vol.device
+        W, H = intrinsic_params(intrinsic)[:2]
+        E = np.asarray(to_numpy(extrinsics), dtype=np.float64).reshape(-1, 4, 4)
+        F = E.shape[0]
+        on_dev = bool(getattr(depth_u16, "is_cuda", False))
+        if self.world_size == 1:
+            chunks = vol.stream_chunks(F, chunk, ramp=self.stream_ramp(1, on_dev))
+            if depth_u16.is_cuda:
+                for f0, f1 in chunks:
+                    vol.integrate_u16_batch(depth_u16[f0:f1], None, intrinsic, E[f0:f1], depth_scale, depth_trunc,
+                                            update_counts=None if update_counts is None else update_counts[f0:f1])
+            else:
+                vol.integrate_host(depth_u16, None, intrinsic, E, depth_scale, depth_trunc, chunk, update_counts)
+            return
+        if vol.color:
+            raise RuntimeError("integrate_stream: colour volumes are not streamed yet (use integrate_batch)")
+        is_src = self.rank == src
+        from_host = is_src and not depth_u16.is_cuda
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream(dev)
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(dev)
+            cs = self._copy_stream
+            with torch.cuda.stream(cs):                           # poses (128 B per frame), off the compute stream
+                hdr = torch.cat([torch.as_tensor(E).reshape(-1), torch.tensor([1.0 if on_dev else 0.0], dtype=torch.float64)])
+                hdr = hdr.to(dev, non_blocking=True)
+                dist.broadcast(hdr, src, group=self.group)
+                hdr = hdr.cpu().numpy()                           # the C ABI takes the poses from host memory
+            E, src_on_dev = hdr[:-1].reshape(-1, 4, 4), bool(hdr[-1] != 0.0)
+            chunks = vol.stream_chunks(F, chunk, ramp=self.stream_ramp(self.world_size, src_on_dev))
+            n = max(f1 - f0 for f0, f1 in chunks)
+            stage = vol._staging(n, H, W, False, count=3)
+            free = vol._stage_free                                # kept across calls (see DenseTSDFVolume._staging)
+
+            dev_src = is_src and not from_host                    # frames already in this rank's HBM: broadcast them in place
+            if dev_src:
+                cs.wait_stream(main)                              # whoever produced them did so on the current stream
+            bufs = {}
+
+            def issue(k):
+                f0, f1 = chunks[k]
+                m = f1 - f0
+                with torch.cuda.stream(cs):
+                    if dev_src:
+                        u16 = depth_u16[f0:f1]
+                    else:
+                        u16 = stage[k % 3][0][:m]
+                        if free[k % 3] is not None:
+                            cs.wait_event(free[k % 3])
+                        if is_src:
+                            u16.copy_(depth_u16[f0:f1], non_blocking=True)
+                    bufs[k] = u16
+                    # the collective is enqueued behind the copy stream's work (NCCL waits for the
+                    # stream that is current at the call); NCCL has no 16-bit integer type: ship bytes
+                    return dist.broadcast(u16.view(torch.uint8), src, group=self.group, async_op=True)
+
+            works = {0: issue(0)}
+            if len(chunks) > 1:
+                works[1] = issue(1)
+            for k, (f0, f1) in enumerate(chunks):
+                if k + 2 < len(chunks):
+                    works[k + 2] = issue(k + 2)
+                works.pop(k).wait()                                # current stream waits for chunk k
+                vol.integrate_u16_batch(bufs.pop(k), None, intrinsic, E[f0:f1], depth_scale, depth_trunc, scratch=stage[k % 3][1],
+                                        update_counts=None if update_counts is None else update_counts[f0:f1])
+                free[k % 3] = torch.cuda.Event()
+                free[k % 3].record(main)
+
     def build_3D_map(self, rgbd, intrinsic, extrinsic):
         self.tsdf.integrate(rgbd, intrinsic, extrinsic)
 

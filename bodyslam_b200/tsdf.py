@@ -152,11 +152,72 @@ class DenseTSDFVolume:
         if not dry_run:
             self.frames_integrated += F
 
+    def integrate_u16_batch(self, depth_u16, color, intrinsic, extrinsics, depth_scale: float = 1000.0, depth_trunc: float = 3.0,
+                            scratch=None, update_counts=None):
+        """F uint16 frames in order with the 3DM depth conversion (slam_utils.py:212-220) fused into
+        the integration's first pass.  depth_u16 [F,H,W] uint16 CUDA; scratch: optional f32 CUDA
+        tensor with >= F*H*W elements that receives the converted frames (returned)."""
+        torch = _lib.require_cuda()
+        if ops._dtype_name(depth_u16) != "uint16":
+            raise RuntimeError("[DenseTSDFVolume::Integrate] Unsupported image format.")
+        depth_u16 = ops.as_cuda(depth_u16, torch.uint16, self.device)
+        if color is not None:
+            color = ops.as_cuda(color, torch.uint8, self.device)
+        depth_u16, (W, H, fx, fy, cx, cy) = self._check_frame(depth_u16, color if self.color else None, intrinsic)
+        F = depth_u16.shape[0]
+        E = np.ascontiguousarray(np.asarray(to_numpy(extrinsics), dtype=np.float64).reshape(-1, 16))
+        if E.shape[0] != F:
+            raise RuntimeError(f"integrate_u16_batch: {F} frames but {E.shape[0]} extrinsics")
+        if scratch is None or scratch.numel() < F * H * W:
+            scratch = torch.empty((F, H, W), dtype=torch.float32, device=self.device)
+        K = np.array([fx, fy, cx, cy], dtype=np.float64)
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.bslam_tsdf_integrate_u16(self._h, _lib.ptr(depth_u16), float(depth_scale), float(depth_trunc or 0.0),
+                                                        _lib.ptr(scratch), _lib.ptr(color) if self.color else None, F, H, W,
+                                                        _lib.ptr(K), _lib.ptr(E), _lib.ptr(update_counts), _lib.stream_ptr(self.device)))
+        self.frames_integrated += F
+        return scratch
+
+    @staticmethod
+    def stream_chunks(F: int, chunk: int = 256, ramp=(32, 64, 128)):
+        """[(f0, f1)] for streamed integration: a short ramp first, so that the compute stream starts
+        after a 32-frame copy instead of a full chunk, then near-equal chunks of at most `chunk`."""
+        out, f = [], 0
+        for r in ramp:
+            if F - f <= chunk or r >= chunk:
+                break
+            out.append((f, f + r))
+            f += r
+        rest = F - f
+        if rest > 0:
+            n = -(-rest // chunk)
+            base, extra = divmod(rest, n)
+            for i in range(n):
+                m = base + (1 if i < extra else 0)
+                out.append((f, f + m))
+                f += m
+        return out
+
+    def _staging(self, n, H, W, use_color, count=2):
+        torch = _lib.require_cuda()
+        key = (n, H, W, use_color, count)
+        if getattr(self, "_stage_key", None) != key:
+            dev = self.device
+            self._stage = [(torch.empty((n, H, W), dtype=torch.uint16, device=dev),
+                            torch.empty((n, H, W), dtype=torch.float32, device=dev),
+                            torch.empty((n, H, W, 3), dtype=torch.uint8, device=dev) if use_color else None)
+                           for _ in range(count)]
+            self._stage_key = key
+            # event per staging buffer: the compute stream is done with it.  Kept across calls, so the
+            # first copies of the next replay overlap the tail of this one instead of waiting for it.
+            self._stage_free = [None] * count
+        return self._stage
+
     def integrate_host(self, depth_u16, color, intrinsic, extrinsics, depth_scale: float = 1000.0, depth_trunc: float = 3.0,
                        chunk: int = 256, update_counts=None):
         """Frames that live in HOST memory (ideally pinned): uint16 depth [F,H,W] (+ uint8 colour
         [F,H,W,3]) are streamed to the device in chunks on a side stream, double-buffered, while
-        the previous chunk is converted (a4) and integrated (K3) on the current stream -- the
+        the previous chunk is converted (a4, fused) and integrated (K3) on the current stream -- the
         shape of `update_map_after_pg` once the PNGs are decoded.  Frame order is preserved.
         """
         torch = _lib.require_cuda()
@@ -177,20 +238,12 @@ class DenseTSDFVolume:
             if getattr(self, "_copy_stream", None) is None:
                 self._copy_stream = torch.cuda.Stream(dev)
             cs = self._copy_stream
-            n = min(chunk, F)
-            key = (n, H, W, use_color)
-            if getattr(self, "_stage_key", None) != key:
-                self._stage = [(torch.empty((n, H, W), dtype=torch.uint16, device=dev),
-                                torch.empty((n, H, W), dtype=torch.float32, device=dev),
-                                torch.empty((n, H, W, 3), dtype=torch.uint8, device=dev) if use_color else None)
-                               for _ in range(2)]
-                self._stage_key = key
-            free = [None, None]      # event: the compute stream is done with staging buffer i
-            cs.wait_stream(main)
-            for k, f0 in enumerate(range(0, F, n)):
-                f1 = min(F, f0 + n)
+            chunks = self.stream_chunks(F, chunk)
+            stage = self._staging(max(f1 - f0 for f0, f1 in chunks), H, W, use_color)
+            free = self._stage_free  # event: the compute stream is done with staging buffer i
+            for k, (f0, f1) in enumerate(chunks):
                 m = f1 - f0
-                u16, f32, col = self._stage[k & 1]
+                u16, f32, col = stage[k & 1]
                 with torch.cuda.stream(cs):
                     if free[k & 1] is not None:
                         cs.wait_event(free[k & 1])
@@ -200,10 +253,8 @@ class DenseTSDFVolume:
                     copied = torch.cuda.Event()
                     copied.record(cs)
                 main.wait_event(copied)
-                _lib.check(self._L.bslam_depth_from_u16(_lib.ptr(u16), m * H * W, float(depth_scale), float(depth_trunc or 0.0),
-                                                        _lib.ptr(f32), _lib.stream_ptr(dev)))
-                self.integrate_batch(f32[:m], col[:m] if use_color else None, intrinsic, E[f0:f1],
-                                     update_counts=None if update_counts is None else update_counts[f0:f1])
+                self.integrate_u16_batch(u16[:m], col[:m] if use_color else None, intrinsic, E[f0:f1], depth_scale, depth_trunc,
+                                         scratch=f32, update_counts=None if update_counts is None else update_counts[f0:f1])
                 free[k & 1] = torch.cuda.Event()
                 free[k & 1].record(main)
 
@@ -219,6 +270,12 @@ class DenseTSDFVolume:
         finally:
             self.color = col
         return counts
+
+    def dry_stats(self, reset: bool = True):
+        """culling statistics of the dry runs since the last reset (see bslam_tsdf_dry_stats) -> dict"""
+        out = (C.c_ulonglong * 4)()
+        _lib.check(self._L.bslam_tsdf_dry_stats(self._h, out, int(bool(reset)), _lib.stream_ptr(self.device)))
+        return {"warp_frame_pairs": int(out[0]), "pairs_in_image": int(out[1]), "pairs_updating": int(out[2]), "voxels_tested": int(out[3])}
 
     def set_batch(self, frames_per_launch: int):
         """frames per integrate launch (0 = library default, max 256)"""

@@ -160,6 +160,18 @@ BSLAM_API int bslam_tsdf_integrate(bslam_volume *vol, const float *d_depth, cons
                                    unsigned long long *d_update_counts, int dry_run,
                                    bslam_stream_t stream);
 
+/*
+ * The replay shape of `update_map_after_pg` (N/3DM/slam_utils.py:124-135) with the frames as they
+ * come off the PNG decoder: uint16 depth in 3DM units.  Fuses `RGBD._read_rgbd_for_tsdf`'s depth
+ * conversion (N/3DM/slam_utils.py:212-220: f32(u16) / depth_scale, >= depth_trunc -> 0) into the
+ * first pass of the integration; d_depth_scratch [F][H][W] f32 receives the converted frames
+ * (what bslam_depth_from_u16 would have produced) and must stay valid until the call's work is done.
+ */
+BSLAM_API int bslam_tsdf_integrate_u16(bslam_volume *vol, const uint16_t *d_depth_u16, float depth_scale,
+                                       float depth_trunc, float *d_depth_scratch, const uint8_t *d_rgb,
+                                       int F, int H, int W, const double *h_K, const double *h_extrinsics,
+                                       unsigned long long *d_update_counts, bslam_stream_t stream);
+
 /* Round-robin z-sharding: this box holds every `stride_bricks`-th 8-voxel brick layer of the
  * grid, starting at global plane gz0 (= 8 * rank): local plane z is global plane
  * gz0 + (z / 8) * 8 * stride_bricks + z % 8.  Balances integration across ranks whatever the
@@ -173,6 +185,11 @@ BSLAM_API int bslam_tsdf_layout(const bslam_volume *vol, size_t *h_offsets /* [4
 /* frames per integrate launch (1..BSLAM_MAX_BATCH, 0 = library default).  Larger batches keep a
  * voxel in registers across more frames; smaller ones keep the batch's depth images L2-resident. */
 BSLAM_API int bslam_tsdf_set_batch(bslam_volume *vol, int frames_per_launch);
+
+/* Culling statistics accumulated by dry runs (bslam_tsdf_integrate with dry_run = 1) since the last
+ * reset: h_stat4 = {(warp, frame) pairs tested, pairs with a voxel projecting into the image, pairs
+ * with an updated voxel, voxels tested}.  Measurement aid for DESIGN.md / bench.py; synchronises. */
+BSLAM_API int bslam_tsdf_dry_stats(bslam_volume *vol, unsigned long long *h_stat4, int reset, bslam_stream_t stream);
 
 /* Device self-test: n random operand triples through the kernels' shared-reciprocal division and
  * magic-number floor, compared with IEEE `/` and (int) casts; returns the number of mismatches

@@ -128,3 +128,16 @@ def test_synthetic_scenes_are_deterministic_and_in_range():
         assert np.array_equal(d1, d2) and d1.dtype == np.uint16 and c1.shape == (2, 120, 160, 3)
         valid = d1 > 0
         assert 0.9 < valid.mean() < 0.995 and d1[valid].min() >= 5 and d1.max() <= 700
+
+
+def test_stream_chunks_cover_all_frames_in_order():
+    from bodyslam_b200.tsdf import DenseTSDFVolume as D
+
+    for F in (1, 7, 255, 256, 257, 600, 1000, 5000):
+        for chunk in (8, 64, 256):
+            ch = D.stream_chunks(F, chunk)
+            assert ch[0][0] == 0 and ch[-1][1] == F
+            assert all(a[1] == b[0] for a, b in zip(ch, ch[1:]))
+            assert all(0 < f1 - f0 <= chunk for f0, f1 in ch)
+    assert D.stream_chunks(1000, 256, ramp=()) == [(0, 250), (250, 500), (500, 750), (750, 1000)]
+    assert [b - a for a, b in D.stream_chunks(1000)][:3] == [32, 64, 128]

@@ -34,6 +34,15 @@ def _worker(rank, world, port, ret, layout):
             E = np.zeros_like(sc["E"])
         sh.integrate_batch(depth, None, sc["intrinsic"], E, broadcast_from=0)
         mesh = sh.extract_mesh()
+        # the streamed replay (pinned host u16 on rank 0 -> H2D -> NCCL broadcast -> fused a4 + integrate,
+        # pipelined over chunks) must build the same shard, and report the same per-frame update counts
+        sh2 = ShardedTSDF(sc["voxel_length"], sc["sdf_trunc"], 128, sc["origin"], color=False, device=dev, rank=rank, world_size=world, layout=layout)
+        counts = torch.zeros(F, dtype=torch.int64, device=dev)
+        src = torch.from_numpy(sc["depth_u16"]).pin_memory() if rank == 0 else None
+        sh2.integrate_stream(src if rank == 0 else torch.empty(0), sc["intrinsic"], sc["E"] if rank == 0 else np.zeros_like(sc["E"]), src=0, chunk=2,
+                             update_counts=counts)
+        same = torch.equal(sh2.tsdf.export_dense()[0], sh.tsdf.export_dense()[0]) and torch.equal(sh2.tsdf.export_dense()[1], sh.tsdf.export_dense()[1])
+        dist.all_reduce(counts)
         if rank == 0:
             ref = DenseTSDFVolume(sc["voxel_length"], sc["sdf_trunc"], 128, sc["origin"], color=False, device=dev)
             ref.integrate_batch(depth, None, sc["intrinsic"], sc["E"])
@@ -44,7 +53,8 @@ def _worker(rank, world, port, ret, layout):
             # the slab itself equals the slice of the full volume
             z0, z1 = sh.bounds[0]
             ok = ok and torch.equal(sh.contiguous_slab().export_dense()[1], ref.export_dense()[1][:, :, z0:z1])
-            ok = ok and sh.layout == layout
+            ok = ok and sh.layout == layout and same
+            ok = ok and counts.cpu().tolist() == ref.count_updates(depth, sc["intrinsic"], sc["E"]).cpu().tolist()
             ret.put(("ok" if ok else "sharded mesh differs from single-GPU mesh", int(rm.triangles.shape[0])))
         else:
             assert mesh is None

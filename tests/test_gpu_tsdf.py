@@ -244,3 +244,50 @@ def test_rgbd_loader_and_update_map_after_pg_from_png_files(cuda, tmp_path):
     from bodyslam_b200.io import read_ply
     v, f = read_ply(str(tmp_path / "m.ply"))
     assert len(v) == mesh.vertices.shape[0] and len(f) == mesh.triangles.shape[0]
+
+
+def test_fused_u16_integrate_equals_a4_then_integrate(cuda):
+    """bslam_tsdf_integrate_u16 (a4 fused into the first pass) == bslam_depth_from_u16 + bslam_tsdf_integrate,
+    bit for bit, and its scratch holds exactly the a4 output; also against the oracle."""
+    from bodyslam_b200 import ops
+    sc = small_scene("laparoscopy512", res=96, frames=5, with_color=False)
+    a, ca = run_gpu(sc, cuda)
+    b = DenseTSDFVolume(sc["voxel_length"], sc["sdf_trunc"], 96, sc["origin"], color=False, device=cuda)
+    cb = torch.zeros(5, dtype=torch.int64, device=cuda)
+    scratch = b.integrate_u16_batch(torch.from_numpy(sc["depth_u16"]).to(cuda), None, sc["intrinsic"], sc["E"], 1000.0, 3.0, update_counts=cb)
+    assert torch.equal(scratch, ops.depth_from_u16(sc["depth_u16"], 1000.0, 3.0, cuda))
+    ta, wa = a.export_dense()
+    tb, wb = b.export_dense()
+    assert torch.equal(ta, tb) and torch.equal(wa, wb)
+    assert np.array_equal(ca, cb.cpu().numpy())
+    V, co = run_oracle(sc)
+    assert np.array_equal(co, cb.cpu().numpy())
+    assert_volume_equal(b, V, sc["sdf_trunc"])
+
+
+@pytest.mark.parametrize("W,H", [(600, 480), (333, 201)])
+def test_fused_u16_integrate_odd_image_sizes(cuda, W, H):
+    """widths that are not a multiple of 4 / 16 take the scalar path of the fused conversion"""
+    sc = small_scene("laparoscopy512", res=64, frames=3, W=W, H=H, with_color=False)
+    vol = DenseTSDFVolume(sc["voxel_length"], sc["sdf_trunc"], 64, sc["origin"], color=False, device=cuda)
+    counts = torch.zeros(3, dtype=torch.int64, device=cuda)
+    vol.integrate_u16_batch(torch.from_numpy(sc["depth_u16"]).to(cuda), None, sc["intrinsic"], sc["E"], update_counts=counts)
+    V, co = run_oracle(sc)
+    assert np.array_equal(co, counts.cpu().numpy())
+    assert_volume_equal(vol, V, sc["sdf_trunc"])
+
+
+def test_integrate_host_ramped_chunks_equal_one_batch(cuda):
+    """streamed host frames (ramp of small chunks first) == one resident batch; counts per frame too"""
+    sc = small_scene("laparoscopy512", res=64, frames=40, with_color=False, frame_ids=np.arange(0, 1000, 25))
+    a, ca = run_gpu(sc, cuda)
+    b = DenseTSDFVolume(sc["voxel_length"], sc["sdf_trunc"], 64, sc["origin"], color=False, device=cuda)
+    cb = torch.zeros(40, dtype=torch.int64, device=cuda)
+    host = torch.from_numpy(sc["depth_u16"]).pin_memory()
+    b.integrate_host(host, None, sc["intrinsic"], sc["E"], chunk=8, update_counts=cb)   # chunks: ramp disabled above chunk, 5 x 8
+    c = DenseTSDFVolume(sc["voxel_length"], sc["sdf_trunc"], 64, sc["origin"], color=False, device=cuda)
+    for f0, f1 in [(0, 3), (3, 10), (10, 40)]:
+        c.integrate_u16_batch(torch.from_numpy(sc["depth_u16"][f0:f1]).to(cuda), None, sc["intrinsic"], sc["E"][f0:f1])
+    for v in (b, c):
+        assert torch.equal(a.export_dense()[0], v.export_dense()[0]) and torch.equal(a.export_dense()[1], v.export_dense()[1])
+    assert np.array_equal(ca, cb.cpu().numpy())
