@@ -79,6 +79,7 @@ struct bslam_volume {
     // optional per-launch timing of the dominant kernel (bslam_tsdf_profile)
     int batch; // frames per integrate launch (0 = default)
     int prof_enabled, prof_n;
+    int zpw;                                  // z layers per integrate warp (0 = auto by shard size)
     static constexpr int kProfPairs = 2048;   // integrate launches timed per bslam_tsdf_profile_read
     cudaEvent_t prof_ev[2 * kProfPairs];
     double prof_ms_accum;

@@ -277,6 +277,10 @@ class DenseTSDFVolume:
         _lib.check(self._L.bslam_tsdf_dry_stats(self._h, out, int(bool(reset)), _lib.stream_ptr(self.device)))
         return {"warp_frame_pairs": int(out[0]), "pairs_in_image": int(out[1]), "pairs_updating": int(out[2]), "voxels_tested": int(out[3])}
 
+    def set_z_split(self, z_layers_per_warp: int):
+        """z layers per integrate warp: 8, 4, 2 or 0 = automatic (see bslam_tsdf_set_z_split)"""
+        _lib.check(self._L.bslam_tsdf_set_z_split(self._h, int(z_layers_per_warp)))
+
     def set_batch(self, frames_per_launch: int):
         """frames per integrate launch (0 = library default, max 256)"""
         _lib.check(self._L.bslam_tsdf_set_batch(self._h, int(frames_per_launch)))

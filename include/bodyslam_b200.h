@@ -186,6 +186,11 @@ BSLAM_API int bslam_tsdf_layout(const bslam_volume *vol, size_t *h_offsets /* [4
  * voxel in registers across more frames; smaller ones keep the batch's depth images L2-resident. */
 BSLAM_API int bslam_tsdf_set_batch(bslam_volume *vol, int frames_per_launch);
 
+/* z layers per integrate warp: a brick's 8 layers are shared by 2 * 8 / n warps.  8 is the most
+ * instruction-efficient; 4 / 2 shorten the serial frame chain of a brick, which bounds the launch
+ * time on small shards (8 GPUs).  0 (default) = chosen from the shard's brick count. */
+BSLAM_API int bslam_tsdf_set_z_split(bslam_volume *vol, int z_layers_per_warp);
+
 /* Culling statistics accumulated by dry runs (bslam_tsdf_integrate with dry_run = 1) since the last
  * reset: h_stat4 = {(warp, frame) pairs tested, pairs with a voxel projecting into the image, pairs
  * with an updated voxel, voxels tested}.  Measurement aid for DESIGN.md / bench.py; synchronises. */

@@ -291,3 +291,21 @@ def test_integrate_host_ramped_chunks_equal_one_batch(cuda):
     for v in (b, c):
         assert torch.equal(a.export_dense()[0], v.export_dense()[0]) and torch.equal(a.export_dense()[1], v.export_dense()[1])
     assert np.array_equal(ca, cb.cpu().numpy())
+
+
+@pytest.mark.parametrize("zpw", [8, 4, 2])
+def test_z_split_variants_are_bit_identical(cuda, zpw):
+    """a brick's 8 layers shared by 2, 4 or 8 warps (bslam_tsdf_set_z_split): same volume, same counts,
+    ragged box (nz not a multiple of 8) and colour included"""
+    sc = small_scene("laparoscopy512", res=72, frames=5)
+    dims = (72, 70, 68)
+    vol = DenseTSDFVolume(sc["voxel_length"], sc["sdf_trunc"], dims, sc["origin"], color=True, device=cuda)
+    vol.set_z_split(zpw)
+    from bodyslam_b200 import ops
+    depth = ops.depth_from_u16(sc["depth_u16"], 1000.0, 3.0, cuda)
+    counts = torch.zeros(5, dtype=torch.int64, device=cuda)
+    vol.integrate_batch(depth, torch.from_numpy(sc["color"]).to(cuda), sc["intrinsic"], sc["E"], update_counts=counts)
+    V, co = run_oracle(sc, color=True, dims=dims)
+    assert np.array_equal(co, counts.cpu().numpy())
+    assert_volume_equal(vol, V, sc["sdf_trunc"], color=True)
+    assert np.array_equal(vol.count_updates(depth, sc["intrinsic"], sc["E"]).cpu().numpy(), co)
