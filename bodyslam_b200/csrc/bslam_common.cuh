@@ -41,7 +41,7 @@ constexpr int kNumSMs = 148;                        // B200
 struct VolView {
     float2 *vox;
     float *color;        // optional: per brick 3 planes of 512 f32 (r, g, b)
-    uint8_t *flags;      // per brick: 1 once any voxel of the brick was updated
+    uint8_t *flags;      // per brick: bit 0 = some voxel was updated, bit 1 = some voxel holds a tsdf != 1 (or was imported)
     int nx, ny, nz, gz0; // logical box; global z of local plane z = gz0 + (z / 8) * 8 * zs + z % 8
     int zs;              // z interleave stride in brick layers (1 = contiguous slab, N = round-robin over N ranks)
     int nbx, nby, nbz;   // bricks per axis (ceil)

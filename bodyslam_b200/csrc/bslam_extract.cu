@@ -4,8 +4,13 @@
 // TSDF.extract_mesh / TSDF.extract_pcd (N/3DM/tsdf.py:39-43); restated in SURVEY.md
 // Appendix A.4/A.5 and checked against oracle/o3d_oracle.c.
 //
-// One CTA per 8^3 brick (512 threads, one per voxel).  Bricks never touched by integration
-// (flag byte 0) exit without reading the volume.  Compaction is count -> prefix sum -> emit:
+// One CTA pass per 8^3 brick (512 threads, one per voxel), and only for SURFACE CANDIDATES: bricks
+// that may hold a tsdf < 1 (flag bit 1, set by the band path of the integration) or whose +x/+y/+z
+// neighbours do -- a cube or an edge with a sign change has a negative corner, and that corner lies
+// in such a brick.  The candidates are compacted in brick order (deterministic output) and walked by
+// a persistent grid, so the cost follows the surface (~10^4 bricks at 512^3), not the volume
+// (2.6 * 10^5), and is low enough for the reference's extract-every-frame cadence
+// (N/3DM/slam.py:126,195).  Compaction is count -> prefix sum -> emit:
 //   * warp ballots give, per 32-voxel chunk and axis, the mask of edges that own a vertex;
 //     popc prefixes of the 48 mask words number the vertices inside a brick;
 //   * a prefix sum over bricks gives each brick's vertex / triangle base;
@@ -28,13 +33,16 @@ struct McScratch {
     uint32_t *ntri;      // [nb]
     uint32_t *vbase;     // [nb] exclusive prefix over bricks
     uint32_t *tbase;     // [nb]
-    unsigned long long *totals; // [2]
+    uint32_t *cand;      // [nb] 1 = surface candidate
+    uint32_t *cbase;     // [nb] exclusive prefix of cand
+    uint32_t *list;      // [nb] candidate bricks, ascending
+    unsigned long long *totals; // [4]: vertices, triangles, candidates, -
 };
 
 static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 static size_t mc_scratch_bytes(size_t nb) {
-    return align_up(nb * kMaskWordsPerBrick * 4, 256) + align_up(nb * kMaskWordsPerBrick * 2, 256) + 4 * align_up(nb * 4, 256) + 256;
+    return align_up(nb * kMaskWordsPerBrick * 4, 256) + align_up(nb * kMaskWordsPerBrick * 2, 256) + 7 * align_up(nb * 4, 256) + 256;
 }
 
 static McScratch carve_mc(void *p0, size_t nb) {
@@ -46,6 +54,9 @@ static McScratch carve_mc(void *p0, size_t nb) {
     s.ntri = (uint32_t *)p; p += align_up(nb * 4, 256);
     s.vbase = (uint32_t *)p; p += align_up(nb * 4, 256);
     s.tbase = (uint32_t *)p; p += align_up(nb * 4, 256);
+    s.cand = (uint32_t *)p; p += align_up(nb * 4, 256);
+    s.cbase = (uint32_t *)p; p += align_up(nb * 4, 256);
+    s.list = (uint32_t *)p; p += align_up(nb * 4, 256);
     s.totals = (unsigned long long *)p;
     return s;
 }
@@ -136,13 +147,12 @@ __global__ void __launch_bounds__(kBrickVox) mc_brick_kernel(const VolView v, do
     __shared__ uint32_t s_mask[kMaskWordsPerBrick];
     __shared__ uint32_t s_pref[kMaskWordsPerBrick];
     __shared__ uint32_t s_wtri[16];
-    const int64_t b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (!v.flags[b]) {
-        if (!EMIT && tid == 0) { sc.nvert[b] = 0; sc.ntri[b] = 0; }
-        return;
-    }
-    if (EMIT && sc.nvert[b] == 0 && sc.ntri[b] == 0) return;
+    const unsigned int n_cand = (unsigned int)sc.totals[2];
+  for (unsigned int ci = blockIdx.x; ci < n_cand; ci += gridDim.x) {      // persistent grid over the candidate list
+    __syncthreads();                                                       // shared buffers of the previous brick are free
+    const int64_t b = sc.list[ci];
+    if (EMIT && sc.nvert[b] == 0 && sc.ntri[b] == 0) continue;
     const int bx = (int)(b % v.nbx), by = (int)((b / v.nbx) % v.nby), bz = (int)(b / ((int64_t)v.nbx * v.nby));
     const BrickClass c = classify_brick(v, halo_lo, halo_hi, bx, by, bz, s_t, s_ok, s_cv);
 
@@ -175,7 +185,7 @@ __global__ void __launch_bounds__(kBrickVox) mc_brick_kernel(const VolView v, do
             sc.vmask[b * kMaskWordsPerBrick + tid] = s_mask[tid];
             sc.vprefix[b * kMaskWordsPerBrick + tid] = (uint16_t)s_pref[tid];
         }
-        return;
+        continue;
     }
     // ---------------- emit vertices
     const int ly = tid & 7, lx = (tid >> 3) & 7, lz = tid >> 6;
@@ -236,35 +246,86 @@ __global__ void __launch_bounds__(kBrickVox) mc_brick_kernel(const VolView v, do
             tris[3 * t_out + 2] = ids[1];
         }
     }
+  }
 }
 
-// exclusive prefix sums over bricks (single CTA; nb <= a few million)
+// exclusive prefix sums over bricks of up to two arrays (single CTA: 8 entries per thread and
+// iteration, warp-shuffle scan + 32 warp totals; 262 144 bricks take 32 iterations)
 __global__ void __launch_bounds__(1024) brick_scan_kernel(const uint32_t *a, const uint32_t *b, uint32_t *abase, uint32_t *bbase, int64_t n,
                                                           unsigned long long *totals) {
-    __shared__ unsigned long long sa[1024], sb[1024];
-    __shared__ unsigned long long ca, cb;
-    if (threadIdx.x == 0) { ca = 0; cb = 0; }
+    __shared__ unsigned long long s_wa[32], s_wb[32];
+    __shared__ unsigned long long s_ca, s_cb;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { s_ca = 0; s_cb = 0; }
     __syncthreads();
-    for (int64_t base = 0; base < n; base += 1024) {
-        const int64_t i = base + threadIdx.x;
-        const unsigned long long va = (i < n) ? a[i] : 0, vb = (i < n && b) ? b[i] : 0;
-        sa[threadIdx.x] = va; sb[threadIdx.x] = vb;
-        __syncthreads();
-        for (int o = 1; o < 1024; o <<= 1) {
-            const unsigned long long ta = (threadIdx.x >= o) ? sa[threadIdx.x - o] : 0, tb = (threadIdx.x >= o) ? sb[threadIdx.x - o] : 0;
-            __syncthreads();
-            sa[threadIdx.x] += ta; sb[threadIdx.x] += tb;
-            __syncthreads();
+    constexpr int kPer = 8;
+    for (int64_t base = 0; base < n; base += 1024 * kPer) {
+        const int64_t i0 = base + (int64_t)threadIdx.x * kPer;
+        uint32_t va[kPer], vb[kPer];
+        unsigned long long la = 0, lb = 0;
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            va[k] = (i0 + k < n) ? a[i0 + k] : 0u;
+            vb[k] = (b && i0 + k < n) ? b[i0 + k] : 0u;
+            la += va[k]; lb += vb[k];
         }
-        if (i < n) {
-            abase[i] = (uint32_t)(ca + sa[threadIdx.x] - va);
-            if (b) bbase[i] = (uint32_t)(cb + sb[threadIdx.x] - vb);
+        unsigned long long ia = la, ib = lb;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+            if (lane >= o) { ia += ta; ib += tb; }
+        }
+        if (lane == 31) { s_wa[wid] = ia; s_wb[wid] = ib; }
+        __syncthreads();
+        if (wid == 0) {
+            const unsigned long long wa = s_wa[lane], wb = s_wb[lane];
+            unsigned long long xa = wa, xb = wb;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long ta = __shfl_up_sync(0xffffffffu, xa, o), tb = __shfl_up_sync(0xffffffffu, xb, o);
+                if (lane >= o) { xa += ta; xb += tb; }
+            }
+            s_wa[lane] = xa - wa; s_wb[lane] = xb - wb;     // exclusive over warps
         }
         __syncthreads();
-        if (threadIdx.x == 1023) { ca += sa[1023]; cb += sb[1023]; }
+        unsigned long long ea = s_ca + s_wa[wid] + ia - la, eb = s_cb + s_wb[wid] + ib - lb;
+#pragma unroll
+        for (int k = 0; k < kPer; ++k) {
+            if (i0 + k < n) {
+                abase[i0 + k] = (uint32_t)ea;
+                if (b) bbase[i0 + k] = (uint32_t)eb;
+            }
+            ea += va[k]; eb += vb[k];
+        }
+        __syncthreads();
+        if (threadIdx.x == 1023) { s_ca = ea; s_cb = eb; }   // the last thread's running sums = totals so far
         __syncthreads();
     }
-    if (threadIdx.x == 0) { totals[0] = ca; totals[1] = cb; }
+    if (threadIdx.x == 0) { totals[0] = s_ca; totals[1] = s_cb; }
+}
+
+// surface candidates: brick b is looked at if any of the 8 bricks b + {0,1}^3 may hold a tsdf < 1
+// (flag bit 1); with a halo plane above, the top brick layer is kept whenever it was touched at
+// all (the slab above keeps its own flags).  Also clears the per-brick counts of the others.
+__global__ void mc_mark_kernel(const VolView v, int have_halo_hi, McScratch sc) {
+    const int64_t nb = brick_count(v);
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (int64_t)gridDim.x * blockDim.x) {
+        const int bx = (int)(b % v.nbx), by = (int)((b / v.nbx) % v.nby), bz = (int)(b / ((int64_t)v.nbx * v.nby));
+        unsigned int any = 0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const int x = bx + (k & 1), y = by + ((k >> 1) & 1), z = bz + (k >> 2);
+            if (x < v.nbx && y < v.nby && z < v.nbz) any |= v.flags[((int64_t)z * v.nby + y) * v.nbx + x] & 2u;
+        }
+        if (have_halo_hi && bz == v.nbz - 1) any |= v.flags[b] & 1u;
+        sc.cand[b] = any ? 1u : 0u;
+        sc.nvert[b] = 0; sc.ntri[b] = 0;
+    }
+}
+
+__global__ void mc_list_kernel(int64_t nb, McScratch sc) {
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (int64_t)gridDim.x * blockDim.x)
+        if (sc.cand[b]) sc.list[sc.cbase[b]] = (uint32_t)b;
 }
 
 // ---------------------------------------------------------------- surface points (A.5)
@@ -291,13 +352,12 @@ template <bool EMIT>
 __global__ void __launch_bounds__(kBrickVox) points_brick_kernel(const VolView v, double vl, McScratch sc, float *points, float *normals,
                                                                   float *colors, int32_t *keys, int64_t cap) {
     __shared__ uint32_t s_w[16];
-    const int64_t b = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    if (!v.flags[b]) {
-        if (!EMIT && tid == 0) sc.nvert[b] = 0;
-        return;
-    }
-    if (EMIT && sc.nvert[b] == 0) return;
+    const unsigned int n_cand = (unsigned int)sc.totals[2];
+  for (unsigned int ci = blockIdx.x; ci < n_cand; ci += gridDim.x) {      // persistent grid over the candidate list
+    __syncthreads();
+    const int64_t b = sc.list[ci];
+    if (EMIT && sc.nvert[b] == 0) continue;
     const int bx = (int)(b % v.nbx), by = (int)((b / v.nbx) % v.nby), bz = (int)(b / ((int64_t)v.nbx * v.nby));
     const int ly = tid & 7, lx = (tid >> 3) & 7, lz = tid >> 6;
     const int X = bx * 8 + lx, Y = by * 8 + ly, Z = bz * 8 + lz;
@@ -330,7 +390,7 @@ __global__ void __launch_bounds__(kBrickVox) points_brick_kernel(const VolView v
         if (!EMIT) sc.nvert[b] = acc;
     }
     __syncthreads();
-    if (!EMIT || !cnt) return;
+    if (!EMIT || !cnt) continue;
     int64_t o = (int64_t)sc.vbase[b] + s_w[wid] + (inc - cnt);
     const double half = vl * 0.5, half_gap = 0.99 * vl;
     const double p0[3] = {half + vl * X, half + vl * Y, half + vl * Z};
@@ -367,7 +427,21 @@ __global__ void __launch_bounds__(kBrickVox) points_brick_kernel(const VolView v
         }
         ++o;
     }
+  }
 }
+
+// candidate list of the volume -> sc.list / sc.totals[2] (shared by marching cubes and point extraction)
+static int build_candidates(bslam_volume *vol, const McScratch &sc, int have_halo_hi, cudaStream_t st) {
+    const int64_t nb = brick_count(vol->v);
+    mc_mark_kernel<<<kNumSMs * 4, 256, 0, st>>>(vol->v, have_halo_hi, sc);
+    BSLAM_LAUNCH_CHECK();
+    brick_scan_kernel<<<1, 1024, 0, st>>>(sc.cand, nullptr, sc.cbase, nullptr, nb, sc.totals + 2);
+    BSLAM_LAUNCH_CHECK();
+    mc_list_kernel<<<kNumSMs * 4, 256, 0, st>>>(nb, sc);
+    BSLAM_LAUNCH_CHECK();
+    return BSLAM_OK;
+}
+constexpr int kExtractGrid = kNumSMs * 3;   // persistent CTAs of 512 threads (3 resident per SM)
 
 static int ensure_mc_scratch(bslam_volume *vol) {
     const size_t nb = (size_t)brick_count(vol->v);
@@ -395,8 +469,10 @@ int bslam_mc_count(bslam_volume *vol, const float *d_halo_lo, const float *d_hal
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t nb = brick_count(vol->v);
     const McScratch sc = carve_mc(vol->mc_scratch, (size_t)nb);
-    mc_brick_kernel<false><<<(unsigned)nb, kBrickVox, 0, st>>>(vol->v, vol->voxel_length_d, (const float2 *)d_halo_lo, (const float2 *)d_halo_hi, sc, nullptr, nullptr,
-                                                                nullptr, 0, nullptr, 0);
+    rc = build_candidates(vol, sc, d_halo_hi != nullptr, st);
+    if (rc) return rc;
+    mc_brick_kernel<false><<<kExtractGrid, kBrickVox, 0, st>>>(vol->v, vol->voxel_length_d, (const float2 *)d_halo_lo, (const float2 *)d_halo_hi, sc, nullptr, nullptr,
+                                                               nullptr, 0, nullptr, 0);
     BSLAM_LAUNCH_CHECK();
     brick_scan_kernel<<<1, 1024, 0, st>>>(sc.nvert, sc.ntri, sc.vbase, sc.tbase, nb, sc.totals);
     BSLAM_LAUNCH_CHECK();
@@ -415,7 +491,7 @@ int bslam_mc_emit(bslam_volume *vol, const float *d_halo_lo, const float *d_halo
     BSLAM_CUDA(cudaSetDevice(vol->device));
     const int64_t nb = brick_count(vol->v);
     const McScratch sc = carve_mc(vol->mc_scratch, (size_t)nb);
-    mc_brick_kernel<true><<<(unsigned)nb, kBrickVox, 0, (cudaStream_t)stream>>>(vol->v, vol->voxel_length_d, (const float2 *)d_halo_lo, (const float2 *)d_halo_hi, sc,
+    mc_brick_kernel<true><<<kExtractGrid, kBrickVox, 0, (cudaStream_t)stream>>>(vol->v, vol->voxel_length_d, (const float2 *)d_halo_lo, (const float2 *)d_halo_hi, sc,
                                                                                  d_vertices, d_keys, d_colors, cap_v, d_tri, cap_t);
     BSLAM_LAUNCH_CHECK();
     return BSLAM_OK;
@@ -430,7 +506,9 @@ int bslam_points_count(bslam_volume *vol, int64_t *h_count, bslam_stream_t strea
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t nb = brick_count(vol->v);
     const McScratch sc = carve_mc(vol->mc_scratch, (size_t)nb);
-    points_brick_kernel<false><<<(unsigned)nb, kBrickVox, 0, st>>>(vol->v, vol->voxel_length_d, sc, nullptr, nullptr, nullptr, nullptr, 0);
+    rc = build_candidates(vol, sc, 0, st);
+    if (rc) return rc;
+    points_brick_kernel<false><<<kExtractGrid, kBrickVox, 0, st>>>(vol->v, vol->voxel_length_d, sc, nullptr, nullptr, nullptr, nullptr, 0);
     BSLAM_LAUNCH_CHECK();
     brick_scan_kernel<<<1, 1024, 0, st>>>(sc.nvert, nullptr, sc.vbase, nullptr, nb, sc.totals);
     BSLAM_LAUNCH_CHECK();
@@ -447,7 +525,7 @@ int bslam_points_emit(bslam_volume *vol, float *d_points, float *d_normals, floa
     BSLAM_CUDA(cudaSetDevice(vol->device));
     const int64_t nb = brick_count(vol->v);
     const McScratch sc = carve_mc(vol->mc_scratch, (size_t)nb);
-    points_brick_kernel<true><<<(unsigned)nb, kBrickVox, 0, (cudaStream_t)stream>>>(vol->v, vol->voxel_length_d, sc, d_points, d_normals, d_colors,
+    points_brick_kernel<true><<<kExtractGrid, kBrickVox, 0, (cudaStream_t)stream>>>(vol->v, vol->voxel_length_d, sc, d_points, d_normals, d_colors,
                                                                                      d_keys, cap);
     BSLAM_LAUNCH_CHECK();
     return BSLAM_OK;
