@@ -412,8 +412,8 @@ def main():
 
     if rank == 0:
         peak, peak_src = load_peaks()
-        # per <=256-frame chunk: depth_stats (+ fused a4), frame_soa, super_cull, brick_cull, order, brick_integrate
-        launches_per_step = 6 * len(chunks)
+        # per <=256-frame chunk: depth_stats (+ fused a4), tmax_mip, frame_soa, super_cull, brick_cull, order, brick_integrate
+        launches_per_step = 7 * len(chunks)
         # the library times up to 2048 integrate launches; use the whole steps it recorded
         steps_timed = k_launches // len(chunks)
         ach = (bytes_algo_local * steps_timed / 1e9) / (k_ms * (steps_timed * len(chunks) / k_launches) / 1e3) if k_ms > 0 and steps_timed else None
