@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--no-mc", action="store_true")
     ap.add_argument("--batch", type=int, default=0, help="frames per integrate launch (0 = library default)")
     ap.add_argument("--color", action="store_true", help="also integrate RGB8 colour (reported as an extra, not the headline)")
+    ap.add_argument("--settle", type=float, default=1.5, help="seconds of untimed steps before the warm-up (device clocks / memory settle)")
     ap.add_argument("--extras", action="store_true", help="also time K1/K2 on BASELINE configs[2] (64 x 1080p) and point extraction")
     return ap.parse_args()
 
@@ -278,6 +279,12 @@ def main():
 
     # ---- device-resident timing
     sampler = ClockSampler(local) if rank == 0 else None
+    # a fresh box runs its first ~second of kernels a few % slow (measured: 3.77 ms per integrate launch in
+    # the first process, 3.66 ms in the third, same code): let the device settle before the W warm-up steps
+    t_settle = time.time()
+    while time.time() - t_settle < args.settle:
+        step(depth_u16)
+        torch.cuda.synchronize()
     for _ in range(args.warmup):
         step(depth_u16)
     vol.profile(True)

@@ -47,7 +47,24 @@ struct VolView {
     int nbx, nby, nbz;   // bricks per axis (ceil)
     float vl, half, trunc, trunc_inv;
     double ox, oy, oz;
+    // ScalableTSDFVolume mode (0 = off): the box consists of whole units of unit_res^3 voxels on the
+    // world unit grid, origin = u0 * unit_len; only units activated by a frame are integrated by it
+    int unit_res, unit_shift, unit_stride;   // unit_res = 1 << unit_shift
+    int u0[3];
+    int nux, nuy, nuz;   // units per axis (z: of the whole grid when the box is a z-shard)
+    double unit_len;
 };
+
+// world position (f32, as Open3D narrows it) of the centre of GLOBAL voxel index g along `axis`:
+// dense: float(f32(half + vl * g) + origin);  unit mode: the same inside the unit that holds g
+// (UniformTSDFVolume of origin = unit index * unit_len, local index g % unit_res)
+template <bool UNIT>
+__device__ __forceinline__ float voxel_centre(const VolView &v, int axis, int g) {
+    const double o = axis == 0 ? v.ox : (axis == 1 ? v.oy : v.oz);
+    if (!UNIT) return (float)((double)(v.half + v.vl * (float)g) + o);
+    const int u = g >> v.unit_shift, l = g & (v.unit_res - 1);
+    return (float)((double)(v.half + v.vl * (float)l) + (double)(v.u0[axis] + u) * v.unit_len);
+}
 
 __host__ __device__ inline int64_t brick_count(const VolView &v) {
     return (int64_t)v.nbx * v.nby * v.nbz;

@@ -31,7 +31,8 @@ class DenseTSDFVolume:
     """
 
     def __init__(self, voxel_length: float, sdf_trunc: float, resolution=512, origin=None, color: bool = True,
-                 device=None, gz0: int = 0, z_total: int | None = None, z_interleave: int = 1):
+                 device=None, gz0: int = 0, z_total: int | None = None, z_interleave: int = 1,
+                 unit_activation: bool = False, unit_resolution: int = 32, depth_sampling_stride: int = 8):
         torch = _lib.require_cuda()
         self._L = _lib.load()
         self.device = ops._device(device)
@@ -56,7 +57,27 @@ class DenseTSDFVolume:
         self.z_interleave = int(z_interleave)
         if self.z_interleave != 1:
             _lib.check(self._L.bslam_tsdf_set_z_interleave(self._h, self.z_interleave))
+        self.unit_activation = bool(unit_activation)
+        if self.unit_activation:
+            self.set_unit_activation(unit_resolution, depth_sampling_stride)
         self.frames_integrated = 0
+
+    def set_unit_activation(self, unit_resolution: int = 32, depth_sampling_stride: int = 8):
+        """ScalableTSDFVolume semantics (what the reference's `TSDF()` builds, tsdf.py:7-12): a frame
+        integrates only the unit_resolution^3 units its stride-sampled depth points (+- sdf_trunc)
+        activate; 0 switches back to the dense UniformTSDFVolume rule.  Raises RuntimeError when the
+        box does not consist of whole units on the world unit grid."""
+        _lib.check(self._L.bslam_tsdf_set_unit_activation(self._h, int(unit_resolution), int(depth_sampling_stride), int(self.z_total)))
+        self.unit_activation = unit_resolution > 0
+        self.unit_resolution, self.depth_sampling_stride = int(unit_resolution), int(depth_sampling_stride)
+
+    @staticmethod
+    def unit_aligned(resolution, voxel_length, origin, unit_resolution: int = 32) -> bool:
+        """can a box with this geometry run in unit-activation mode?"""
+        res = (int(resolution),) * 3 if np.isscalar(resolution) else tuple(int(r) for r in resolution)
+        ul = float(voxel_length) * unit_resolution
+        o = np.asarray(origin, dtype=np.float64)
+        return all(r % unit_resolution == 0 for r in res) and bool(np.all(np.abs(np.rint(o / ul) * ul - o) <= 1e-9 * np.maximum(1.0, np.abs(o))))
 
     def storage_layers(self):
         """views of the storage as brick layers: dict(vox [nbz, bytes], flags [nbz, nbx*nby][, color [nbz, bytes]]).
@@ -85,7 +106,8 @@ class DenseTSDFVolume:
         """`deepcopy(self.tsdf)` of tsdf.py:24 -> device-to-device clone."""
         torch = _lib.require_cuda()
         other = DenseTSDFVolume(self.voxel_length, self.sdf_trunc, (self.nx, self.ny, self.nz), self.origin, self.color,
-                                self.device, self.gz0, self.z_total, self.z_interleave)
+                                self.device, self.gz0, self.z_total, self.z_interleave, self.unit_activation,
+                                getattr(self, "unit_resolution", 32), getattr(self, "depth_sampling_stride", 8))
         with torch.cuda.device(self.device):
             _lib.check(self._L.bslam_tsdf_copy(self._h, other._h, _lib.stream_ptr(self.device)))
         other.frames_integrated = self.frames_integrated
@@ -366,9 +388,18 @@ class TSDF:
     """Drop-in for the reference's `TSDF` (N/3DM/tsdf.py:5-52)."""
 
     def __init__(self, voxel_length: float = 0.001, sdf_trunc: float = 0.1, resolution=512, origin=None,
-                 color: bool = True, device=None):
+                 color: bool = True, device=None, unit_activation=None):
+        """unit_activation: True = ScalableTSDFVolume semantics (volume_unit_resolution 32, depth_sampling_stride
+        8, tsdf.py:11-12): a frame only integrates the 32^3 units its sampled depth points activate, exactly
+        what the reference object does; False = every voxel of the box follows the UniformTSDFVolume rule
+        (the dense form BASELINE.json's north_star asks for).  None (default): True when the box consists
+        of whole units on the world unit grid (the default 512^3 box does), else False."""
+        res = (int(resolution),) * 3 if np.isscalar(resolution) else tuple(int(r) for r in resolution)
+        org = origin if origin is not None else tuple(-0.5 * r * voxel_length for r in res)
+        if unit_activation is None:
+            unit_activation = DenseTSDFVolume.unit_aligned(res, voxel_length, org)
         self.tsdf = DenseTSDFVolume(voxel_length=voxel_length, sdf_trunc=sdf_trunc, resolution=resolution, origin=origin,
-                                    color=color, device=device)
+                                    color=color, device=device, unit_activation=bool(unit_activation))
 
     def build_3D_map(self, rgbd, intrinsic, extrinsic):
         '''

@@ -186,6 +186,18 @@ BSLAM_API int bslam_tsdf_layout(const bslam_volume *vol, size_t *h_offsets /* [4
  * voxel in registers across more frames; smaller ones keep the batch's depth images L2-resident. */
 BSLAM_API int bslam_tsdf_set_batch(bslam_volume *vol, int frames_per_launch);
 
+/*
+ * ScalableTSDFVolume semantics -- the volume `TSDF.__init__` literally constructs (N/3DM/tsdf.py:7-12:
+ * volume_unit_resolution = 32, depth_sampling_stride = 8).  With unit_resolution > 0 a frame only
+ * integrates the unit_resolution^3-voxel units activated by its stride-sampled, back-projected
+ * depth points (+- sdf_trunc), and voxel centres are evaluated per unit like Open3D's per-unit
+ * UniformTSDFVolume; everything else stays weight 0 exactly like the sparse reference.  The grid
+ * must consist of whole units on the world unit grid (origin = k * unit_resolution * voxel_length);
+ * z_total: plane count of the whole grid when this volume is a z-shard (0 = nz).  0 switches back
+ * to the dense UniformTSDFVolume semantics (default).
+ */
+BSLAM_API int bslam_tsdf_set_unit_activation(bslam_volume *vol, int unit_resolution, int depth_sampling_stride, int z_total);
+
 /* z layers per integrate warp: a brick's 8 layers are shared by 2 * 8 / n warps.  8 is the most
  * instruction-efficient; 4 / 2 shorten the serial frame chain of a brick, which bounds the launch
  * time on small shards (8 GPUs).  0 (default) = chosen from the shard's brick count. */

@@ -33,6 +33,10 @@ def lib():
         L.orc_tsdf_integrate.restype = C.c_int64
         L.orc_tsdf_integrate.argtypes = [p, p, p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
                                          p, p, p, C.c_int, C.c_int, p, p, C.c_int]
+        L.orc_invert4x4.argtypes = [p, p]
+        L.orc_scalable_integrate.restype = C.c_int64
+        L.orc_scalable_integrate.argtypes = [p, p, p, C.c_int, C.c_int, C.c_int, p, C.c_int, C.c_int, C.c_double, C.c_double,
+                                             p, p, C.c_int, C.c_int, p, p, p, C.c_int, p]
         L.orc_extract_mesh.argtypes = [p, p, p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, p,
                                        p, p, p, C.c_int64, p, p, C.c_int64, p]
         L.orc_extract_points.restype = C.c_int64
@@ -110,6 +114,28 @@ class Volume:
         return lib().orc_tsdf_integrate(_ptr(self.tsdf), _ptr(self.weight), _ptr(self.color if c is not None else None),
                                         self.nx, self.ny, self.nz, self.gz0, self.voxel_length, self.sdf_trunc,
                                         _ptr(self.origin), _ptr(d), _ptr(c), W, H, _ptr(Kd), _ptr(E), int(z_restart))
+
+    def integrate_scalable(self, depth_f32, K, extrinsic, rgb=None, z_restart=8, unit_res=32, stride=8, return_touched=False):
+        """ScalableTSDFVolume.integrate (A.3 step 7; what `TSDF()` of N/3DM/tsdf.py:7-12 builds) on this dense
+        box, which must consist of whole units aligned to the world unit grid (origin = k * unit_length)."""
+        d = np.ascontiguousarray(depth_f32, dtype=np.float32)
+        H, W = d.shape
+        Kd = np.ascontiguousarray(K, dtype=np.float64)
+        E = np.ascontiguousarray(extrinsic, dtype=np.float64)
+        M = np.zeros(16)
+        lib().orc_invert4x4(_ptr(E), _ptr(M))      # Eigen's 4x4 inverse is the cofactor formula
+        c = None if rgb is None else np.ascontiguousarray(rgb, dtype=np.uint8)
+        ul = self.voxel_length * unit_res
+        u0 = np.rint(self.origin / ul)
+        if self.gz0 or np.abs(u0 * ul - self.origin).max() > 1e-9 * max(1.0, np.abs(self.origin).max()) or any(
+                n % unit_res for n in (self.nx, self.ny, self.nz)):
+            raise ValueError("scalable mode needs a box of whole units on the world unit grid")
+        u0 = np.ascontiguousarray(u0, dtype=np.int32)
+        touched = np.zeros((self.nx // unit_res) * (self.ny // unit_res) * (self.nz // unit_res), np.uint8)
+        n = lib().orc_scalable_integrate(_ptr(self.tsdf), _ptr(self.weight), _ptr(self.color if c is not None else None),
+                                         self.nx, self.ny, self.nz, _ptr(u0), int(unit_res), int(stride), self.voxel_length,
+                                         self.sdf_trunc, _ptr(d), _ptr(c), W, H, _ptr(Kd), _ptr(E), _ptr(M), int(z_restart), _ptr(touched))
+        return (n, touched.reshape(self.nx // unit_res, self.ny // unit_res, self.nz // unit_res)) if return_touched else n
 
     def grid(self, name="tsdf"):
         return getattr(self, name).reshape(self.nx, self.ny, self.nz)

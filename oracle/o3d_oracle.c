@@ -12,6 +12,7 @@
  *   orc_backproject      <- PointCloud.create_from_depth_image / pixel_to_3d
  *                           N/3DM/mapping_module.py:37,41 ; N/3DM/scaling_system.py:72-77 (A.2)
  *   orc_tsdf_integrate   <- TSDF.build_3D_map -> volume.integrate   N/3DM/tsdf.py:14-22 (A.3)
+ *   orc_scalable_integrate <- the same through ScalableTSDFVolume (unit activation, A.3 step 7)
  *   orc_extract_mesh     <- TSDF.extract_mesh                       N/3DM/tsdf.py:42-43 (A.4)
  *   orc_extract_points   <- TSDF.extract_pcd                        N/3DM/tsdf.py:39-40 (A.5)
  *
@@ -176,6 +177,137 @@ ORC_API int64_t orc_tsdf_integrate(float *tsdf, float *weight, float *color, int
             }
         }
     }
+    return updated;
+}
+
+/* Eigen's Matrix4d::inverse() is the cofactor (adjugate / determinant) formula; row-major f64 */
+ORC_API void orc_invert4x4(const double *a, double *out) {
+    double c[16];
+    for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+            /* minor of (j, i) -> adjugate entry (i, j) */
+            double m[9];
+            int k = 0;
+            for (int r = 0; r < 4; ++r) {
+                if (r == j) continue;
+                for (int q = 0; q < 4; ++q) {
+                    if (q == i) continue;
+                    m[k++] = a[4 * r + q];
+                }
+            }
+            const double det3 = m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+            c[4 * i + j] = ((i + j) & 1) ? -det3 : det3;
+        }
+    const double det = a[0] * c[0] + a[1] * c[4] + a[2] * c[8] + a[3] * c[12];
+    for (int i = 0; i < 16; ++i) out[i] = c[i] / det;
+}
+
+/* ------------------------------------------------------------------ A.3 step 7 */
+/*
+ * ScalableTSDFVolume::Integrate (the volume `TSDF.__init__` literally builds, N/3DM/tsdf.py:7-12:
+ * volume_unit_resolution = 32, depth_sampling_stride = 8), restated on a dense box made of whole
+ * units: the box origin is unit0 * unit_length (unit_length = voxel_length * unit_res, f64) and
+ * nx, ny, nz are multiples of unit_res.  Units outside the box are ignored (the reference's
+ * volume is unbounded; the build's is not).
+ *   1. points = CreateFromDepthImage(depth f32, K, extrinsic, stride) in world space, f64 (A.2);
+ *   2. every unit with index in floor((p - trunc) / unit_length) .. floor((p + trunc) / unit_length)
+ *      (inclusive, per axis) is opened and integrated ONCE for this frame;
+ *   3. a unit is a UniformTSDFVolume(length = unit_length, resolution = unit_res,
+ *      origin = index * unit_length): A.3 steps 2-6 with x, y, z local to the unit.
+ * z_restart as in orc_tsdf_integrate (applied to the unit-local z; unit_res is a multiple of 8).
+ * touched_out: optional [nux*nuy*nuz] bytes ((ux*nuy + uy)*nuz + uz), 1 = integrated this frame.
+ * Returns the number of voxels updated.
+ */
+ORC_API int64_t orc_scalable_integrate(float *tsdf, float *weight, float *color, int nx, int ny, int nz,
+                                       const int *unit0, int unit_res, int stride, double voxel_length,
+                                       double sdf_trunc, const float *depth, const uint8_t *rgb, int W, int H,
+                                       const double *K, const double *extrinsic, const double *cam_to_world,
+                                       int z_restart, uint8_t *touched_out) {
+    const int nux = nx / unit_res, nuy = ny / unit_res, nuz = nz / unit_res;
+    const double unit_length = voxel_length * (double)unit_res;
+    uint8_t *touched = (uint8_t *)calloc((size_t)nux * nuy * nuz, 1);
+    {
+        const double fxd = K[0], fyd = K[1], cxd = K[2], cyd = K[3];
+        const double *M = cam_to_world;
+        for (int i = 0; i < H; i += stride)
+            for (int j = 0; j < W; j += stride) {
+                const float p = depth[(size_t)i * W + j];
+                if (!(p > 0)) continue;
+                const double z = (double)p;
+                const double x = (j - cxd) * z / fxd;
+                const double y = (i - cyd) * z / fyd;
+                int lo[3], hi[3];
+                for (int r = 0; r < 3; ++r) {
+                    const double w = ((M[4 * r + 0] * x + M[4 * r + 1] * y) + M[4 * r + 2] * z) + M[4 * r + 3];
+                    lo[r] = (int)floor((w - sdf_trunc) / unit_length) - unit0[r];
+                    hi[r] = (int)floor((w + sdf_trunc) / unit_length) - unit0[r];
+                }
+                const int n[3] = {nux, nuy, nuz};
+                for (int r = 0; r < 3; ++r) { if (lo[r] < 0) lo[r] = 0; if (hi[r] > n[r] - 1) hi[r] = n[r] - 1; }
+                for (int ux = lo[0]; ux <= hi[0]; ++ux)
+                    for (int uy = lo[1]; uy <= hi[1]; ++uy)
+                        for (int uz = lo[2]; uz <= hi[2]; ++uz) touched[((size_t)ux * nuy + uy) * nuz + uz] = 1;
+            }
+    }
+    const float fx = (float)K[0], fy = (float)K[1], cx = (float)K[2], cy = (float)K[3];
+    float E[16];
+    for (int i = 0; i < 16; ++i) E[i] = (float)extrinsic[i];
+    const float vl = (float)voxel_length;
+    const float half = vl * 0.5f;
+    const float trunc_f = (float)sdf_trunc;
+    const float trunc_inv = 1.0f / trunc_f;
+    const float dzx = E[2] * vl, dzy = E[6] * vl, dzz = E[10] * vl;
+    const float safe_w = W - 0.0001f, safe_h = H - 0.0001f;
+    const float fxi = 1.0f / fx, fyi = 1.0f / fy;
+    int64_t updated = 0;
+    const int n_units = nux * nuy * nuz;
+#pragma omp parallel for schedule(dynamic) reduction(+ : updated)
+    for (int u = 0; u < n_units; ++u) {
+        if (!touched[u]) continue;
+        const int uz = u % nuz, uy = (u / nuz) % nuy, ux = u / (nuz * nuy);
+        const double org[3] = {(double)(unit0[0] + ux) * unit_length, (double)(unit0[1] + uy) * unit_length,
+                               (double)(unit0[2] + uz) * unit_length};
+        for (int x = 0; x < unit_res; ++x)
+            for (int y = 0; y < unit_res; ++y) {
+                const float px = (float)((double)(half + vl * (float)x) + org[0]);
+                const float py = (float)((double)(half + vl * (float)y) + org[1]);
+                float pcx = 0.f, pcy = 0.f, pcz = 0.f;
+                for (int z = 0; z < unit_res; ++z) {
+                    if (z == 0 || (z_restart > 0 && z % z_restart == 0)) {
+                        const float pz = (float)((double)(half + vl * (float)z) + org[2]);
+                        pcx = ((E[0] * px + E[1] * py) + E[2] * pz) + E[3];
+                        pcy = ((E[4] * px + E[5] * py) + E[6] * pz) + E[7];
+                        pcz = ((E[8] * px + E[9] * py) + E[10] * pz) + E[11];
+                    }
+                    const float cxp = pcx, cyp = pcy, czp = pcz;
+                    pcx += dzx; pcy += dzy; pcz += dzz;
+                    if (czp <= 0) continue;
+                    const float u_f = cxp * fx / czp + cx + 0.5f;
+                    const float v_f = cyp * fy / czp + cy + 0.5f;
+                    if (!(u_f >= 0.0001f && u_f < safe_w && v_f >= 0.0001f && v_f < safe_h)) continue;
+                    const int uu = (int)u_f, vv = (int)v_f;
+                    const float d = depth[(size_t)vv * W + uu];
+                    if (d <= 0.0f) continue;
+                    const float xx = ((float)uu - cx) * fxi, yy = ((float)vv - cy) * fyi;
+                    const float mult = sqrtf((xx * xx + yy * yy) + 1.0f);
+                    const float sdf = (d - czp) * mult;
+                    if (sdf > -trunc_f) {
+                        const size_t idx = ((size_t)(ux * unit_res + x) * ny + (uy * unit_res + y)) * nz + (uz * unit_res + z);
+                        const float t = fminf(1.0f, sdf * trunc_inv);
+                        const float w = weight[idx];
+                        if (color && rgb) {
+                            const uint8_t *c = rgb + ((size_t)vv * W + uu) * 3;
+                            for (int k = 0; k < 3; ++k) color[3 * idx + k] = (color[3 * idx + k] * w + (float)c[k]) / (w + 1.0f);
+                        }
+                        tsdf[idx] = (tsdf[idx] * w + t) / (w + 1.0f);
+                        weight[idx] = w + 1.0f;
+                        ++updated;
+                    }
+                }
+            }
+    }
+    if (touched_out) memcpy(touched_out, touched, (size_t)n_units);
+    free(touched);
     return updated;
 }
 

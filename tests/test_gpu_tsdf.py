@@ -161,7 +161,8 @@ def test_dry_run_counts_leave_volume_untouched(cuda):
 
 def test_tsdf_dropin_api_and_errors(cuda):
     sc = small_scene("laparoscopy512", res=64, frames=2)
-    tsdf = TSDF(voxel_length=sc["voxel_length"], sdf_trunc=sc["sdf_trunc"], resolution=64, origin=sc["origin"], device=cuda)
+    tsdf = TSDF(voxel_length=sc["voxel_length"], sdf_trunc=sc["sdf_trunc"], resolution=64, origin=sc["origin"], device=cuda,
+                unit_activation=False)
     rgbd = RGBDImage.create_from_color_and_depth(sc["color"][0], sc["depth_u16"][0], depth_scale=1000, depth_trunc=3.0,
                                                  convert_rgb_to_intensity=False)
     tsdf.build_3D_map(rgbd, sc["intrinsic"], sc["E"][0])
@@ -228,11 +229,13 @@ def test_rgbd_loader_and_update_map_after_pg_from_png_files(cuda, tmp_path):
     jet = cv2.applyColorMap(oracle.mdem.minmax_u8(sc["depth_u16"][0]), cv2.COLORMAP_JET)
     assert np.array_equal(fr.colored_depth.cpu().numpy(), jet)
     tsdf = update_map_after_pg(list(sc["E"]), rgb_paths, depth_paths, 1000, "CUDA:0", sc["intrinsic"],
-                               voxel_length=sc["voxel_length"], sdf_trunc=sc["sdf_trunc"], resolution=64, origin=sc["origin"])
+                               voxel_length=sc["voxel_length"], sdf_trunc=sc["sdf_trunc"], resolution=64, origin=sc["origin"],
+                               unit_activation=False)
     V, _ = run_oracle(sc, color=True)
     assert_volume_equal(tsdf.tsdf, V, sc["sdf_trunc"], color=True)
     # frame-by-frame through the drop-in classes gives the same map
-    t2 = TSDF(voxel_length=sc["voxel_length"], sdf_trunc=sc["sdf_trunc"], resolution=64, origin=sc["origin"], device=cuda)
+    t2 = TSDF(voxel_length=sc["voxel_length"], sdf_trunc=sc["sdf_trunc"], resolution=64, origin=sc["origin"], device=cuda,
+              unit_activation=False)
     for i in range(5):
         t2.build_3D_map(RGBD(rgb_paths[i], depth_paths[i], "CUDA:0").rgbd_tsdf, sc["intrinsic"], sc["E"][i])
     for x, y in zip(tsdf.tsdf.export_dense(True), t2.tsdf.export_dense(True)):
@@ -309,3 +312,54 @@ def test_z_split_variants_are_bit_identical(cuda, zpw):
     assert np.array_equal(co, counts.cpu().numpy())
     assert_volume_equal(vol, V, sc["sdf_trunc"], color=True)
     assert np.array_equal(vol.count_updates(depth, sc["intrinsic"], sc["E"]).cpu().numpy(), co)
+
+
+@pytest.mark.parametrize("scene,res,trunc_mul", [("laparoscopy512", 128, 1.0), ("laparoscopy512", 128, 8.0), ("colonoscopy256", 64, 1.0)])
+def test_unit_activation_matches_scalable_oracle(cuda, scene, res, trunc_mul):
+    """ScalableTSDFVolume semantics (what the reference's TSDF() builds, N/3DM/tsdf.py:7-12): per frame only
+    the 32^3 units activated by the stride-8 back-projected points +- sdf_trunc are integrated, voxel
+    centres evaluated per unit.  Bit-exact against the oracle's restatement (A.3 step 7): activated-voxel
+    sets, weights, per-frame counts, tsdf, colour; and different from the dense rule."""
+    sc = small_scene(scene, res=res, frames=5)
+    trunc = sc["sdf_trunc"] * trunc_mul
+    ul = sc["voxel_length"] * 32
+    sc["origin"] = np.floor(sc["origin"] / ul + 0.5) * ul        # the box must sit on the world unit grid
+    vol = DenseTSDFVolume(sc["voxel_length"], trunc, res, sc["origin"], color=True, device=cuda, unit_activation=True)
+    from bodyslam_b200 import ops
+    depth = ops.depth_from_u16(sc["depth_u16"], 1000.0, 3.0, cuda)
+    counts = torch.zeros(5, dtype=torch.int64, device=cuda)
+    vol.integrate_batch(depth, torch.from_numpy(sc["color"]).to(cuda), sc["intrinsic"], sc["E"], update_counts=counts)
+    V = oracle.o3d.Volume(res, sc["voxel_length"], trunc, sc["origin"], with_color=True)
+    D = oracle.o3d.Volume(res, sc["voxel_length"], trunc, sc["origin"])
+    co = []
+    for i in range(5):
+        d = oracle.o3d.depth_from_u16(sc["depth_u16"][i])
+        co.append(V.integrate_scalable(d, sc["K"], sc["E"][i], rgb=sc["color"][i]))
+        D.integrate(d, sc["K"], sc["E"][i])
+    assert counts.cpu().tolist() == co
+    assert_volume_equal(vol, V, trunc, color=True)
+    assert V.occupied() <= D.occupied() and (scene != "laparoscopy512" or V.occupied() < D.occupied()), \
+        "unit activation must leave un-activated space untouched"
+    # frame by frame (the SLAM loop) gives the same map as the batch; deepcopy keeps the mode
+    t = TSDF(voxel_length=sc["voxel_length"], sdf_trunc=trunc, resolution=res, origin=sc["origin"], device=cuda)
+    assert t.tsdf.unit_activation
+    for i in range(5):
+        t.tsdf = t.build_copy_3D_map(RGBDImage(sc["color"][i], depth[i]), sc["intrinsic"], sc["E"][i])
+    for x, y in zip(vol.export_dense(True), t.tsdf.export_dense(True)):
+        assert torch.equal(x, y)
+    # extraction on the sparse-activated volume equals the oracle's
+    mesh, ref = vol.extract_triangle_mesh(), V.extract_mesh()
+    from util import canon_mesh
+    a = canon_mesh(mesh.vertices.cpu().numpy(), mesh.vertex_keys.cpu().numpy(), mesh.triangles.cpu().numpy(), (res,) * 3)
+    b = canon_mesh(ref["vertices"], ref["keys"], ref["triangles"], (res,) * 3)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2])
+
+
+def test_unit_activation_needs_an_aligned_box(cuda):
+    with pytest.raises(RuntimeError, match="whole 32\\^3 units|multiple of the unit length"):
+        DenseTSDFVolume(0.004, 0.02, 72, (-0.144,) * 3, color=False, device=cuda, unit_activation=True)
+    with pytest.raises(RuntimeError, match="multiple of the unit length"):
+        DenseTSDFVolume(0.004, 0.02, 64, (-0.1,) * 3, color=False, device=cuda, unit_activation=True)
+    # the drop-in falls back to the dense rule when the box cannot hold whole units
+    assert not TSDF(voxel_length=0.004, sdf_trunc=0.02, resolution=72, device=cuda, color=False).tsdf.unit_activation
+    assert TSDF(voxel_length=0.004, sdf_trunc=0.02, resolution=64, device=cuda, color=False).tsdf.unit_activation
