@@ -282,9 +282,13 @@ def main():
     # a fresh box runs its first ~second of kernels a few % slow (measured: 3.77 ms per integrate launch in
     # the first process, 3.66 ms in the third, same code): let the device settle before the W warm-up steps
     t_settle = time.time()
-    while time.time() - t_settle < args.settle:
+    step(depth_u16)
+    torch.cuda.synchronize()
+    n_settle = torch.tensor([int(args.settle / max(time.time() - t_settle, 1e-3))], device=dev)
+    if world > 1:
+        dist.broadcast(n_settle, 0)          # every rank must run the same number of (collective) steps
+    for _ in range(int(n_settle.item())):
         step(depth_u16)
-        torch.cuda.synchronize()
     for _ in range(args.warmup):
         step(depth_u16)
     vol.profile(True)
