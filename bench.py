@@ -143,6 +143,11 @@ def workload(args):
     return cfg, F, E, res, cfg["voxel_length"] * scale, cfg["sdf_trunc"] * scale
 
 
+def workload_name(F, W, H, res, vl, trunc):
+    return (f"{WORKLOAD}: {F}-frame synthetic laparoscopy sweep, {W}x{H} u16 depth -> {res}^3 TSDF @ {vl * 1e3:g} mm, "
+            f"sdf_trunc {trunc * 1e3:g} mm (BASELINE configs[3])")
+
+
 def cpu_sample(cfg, E, depth_u16_np, frame_ids, res, vl, trunc, budget_s=12.0, max_frames=24):
     """time the oracle (Open3D-equivalent dense integrate, all host threads) on sample frames"""
     import oracle
@@ -194,7 +199,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{WORKLOAD}: {len(E)}-frame synthetic laparoscopy sweep, 640x480 depth -> {res}^3 TSDF @ {vl * 1e3:g} mm",
+            "config": {"workload": workload_name(len(E), cfg["W"], cfg["H"], res, vl, trunc), "frames_per_step": len(E),
                        "reference_arm": "CPU restatement of Open3D UniformTSDFVolume.integrate (oracle/o3d_oracle.c, OpenMP); "
                                         "Open3D itself is not installable offline"},
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -433,8 +438,7 @@ def main():
             "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{WORKLOAD}: {F}-frame synthetic laparoscopy sweep, {W}x{H} u16 depth -> {res}^3 TSDF @ {vl * 1e3:g} mm, "
-                                   f"sdf_trunc {trunc * 1e3:g} mm (BASELINE configs[3])",
+            "config": {"workload": workload_name(F, W, H, res, vl, trunc),
                        "frames_per_step": F, "step": "a4 depth scaling (fused into the first pass) + K3 integrate of all frames, volume resident",
                        "culling": {"voxels_tested_per_frame": cull["voxels_tested"] / F, "updated_over_tested": (int(uf_local.sum().item()) / cull["voxels_tested"]) if cull["voxels_tested"] else None},
                        "l2": "inputs larger than L2 (1.2 GB depth + 1.1 GB volume per step vs 126 MB)",

@@ -40,6 +40,7 @@ _SIGNATURES = {
     "bslam_tsdf_layout": (C.c_int, [_p, _p]),
     "bslam_tsdf_set_batch": (C.c_int, [_p, C.c_int]),
     "bslam_tsdf_set_unit_activation": (C.c_int, [_p, C.c_int, C.c_int, C.c_int]),
+    "bslam_tsdf_chain_histogram": (C.c_int, [_p, _p, _p]),
     "bslam_tsdf_set_z_split": (C.c_int, [_p, C.c_int]),
     "bslam_tsdf_dry_stats": (C.c_int, [_p, _p, C.c_int, _p]),
     "bslam_selftest": (C.c_int, [C.c_ulonglong, C.c_uint, _p, _p]),

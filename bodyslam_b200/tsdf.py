@@ -299,6 +299,12 @@ class DenseTSDFVolume:
         _lib.check(self._L.bslam_tsdf_dry_stats(self._h, out, int(bool(reset)), _lib.stream_ptr(self.device)))
         return {"warp_frame_pairs": int(out[0]), "pairs_in_image": int(out[1]), "pairs_updating": int(out[2]), "voxels_tested": int(out[3])}
 
+    def chain_histogram(self):
+        """active bricks of the last integrate launch by number of active frames (32 buckets of 8 frames)"""
+        out = (C.c_uint * 32)()
+        _lib.check(self._L.bslam_tsdf_chain_histogram(self._h, out, _lib.stream_ptr(self.device)))
+        return list(out)
+
     def set_z_split(self, z_layers_per_warp: int):
         """z layers per integrate warp: 8, 4, 2 or 0 = automatic (see bslam_tsdf_set_z_split)"""
         _lib.check(self._L.bslam_tsdf_set_z_split(self._h, int(z_layers_per_warp)))

@@ -198,6 +198,10 @@ BSLAM_API int bslam_tsdf_set_batch(bslam_volume *vol, int frames_per_launch);
  */
 BSLAM_API int bslam_tsdf_set_unit_activation(bslam_volume *vol, int unit_resolution, int depth_sampling_stride, int z_total);
 
+/* Chain-length histogram of the last integrate launch: h_hist32[k] = active bricks with 8k+1 .. 8k+8
+ * active frames (measurement aid; synchronises). */
+BSLAM_API int bslam_tsdf_chain_histogram(bslam_volume *vol, unsigned int *h_hist32, bslam_stream_t stream);
+
 /* z layers per integrate warp: a brick's 8 layers are shared by 2 * 8 / n warps.  8 is the most
  * instruction-efficient; 4 / 2 shorten the serial frame chain of a brick, which bounds the launch
  * time on small shards (8 GPUs).  0 (default) = chosen from the shard's brick count. */
