@@ -316,17 +316,24 @@ def main():
               f"{k_launches} launches, U_f mean {uf_total / F:.0f} voxels/frame", file=sys.stderr)
 
     # ---- end to end: pinned host buffers -> H2D -> a4 -> K3 -> D2H of the per-frame update counts
-    host_u16 = torch.empty((F, H, W), dtype=torch.uint16).pin_memory() if rank == 0 else None
+    # N = 1: the whole trajectory in pinned host memory.  N > 1: sharded ingest -- every rank holds 1/N of
+    # each chunk in ITS pinned host memory (as N decoder processes would), copies it over its own PCIe link
+    # and the pieces are all-gathered over NVLink; a single host buffer on rank 0 would cap the job at one
+    # link's 53 GB/s (86 k frames/s).  h2d_bytes_per_step counts all ranks.
+    share = ShardedTSDF.ingest_share(F, rank, world, chunk)
+    host_u16 = torch.empty((len(share), H, W), dtype=torch.uint16).pin_memory()
     host_counts = torch.empty(F, dtype=torch.int64).pin_memory()
-    if rank == 0:
-        host_u16.copy_(depth_u16)
+    host_u16.copy_(depth_u16.view(torch.int16)[torch.as_tensor(share, device=dev)].view(torch.uint16))   # (depth_u16 was broadcast above)
     counts = torch.zeros(F, dtype=torch.int64, device=dev)
 
     def e2e_step():
-        # public API: pinned host frames in (rank 0), per-frame update counts out; H2D, broadcast and
-        # integration are pipelined chunk by chunk inside integrate_stream
+        # public API: pinned host frames in, per-frame update counts out; H2D, NVLink exchange and
+        # integration are pipelined chunk by chunk inside integrate_stream(_sharded)
         counts.zero_()
-        step(host_u16, counts)
+        if world == 1:
+            step(host_u16, counts)
+        else:
+            sh.integrate_stream_sharded(host_u16, intr, E, depth_scale=1000.0, depth_trunc=3.0, chunk=chunk, update_counts=counts)
         host_counts.copy_(counts, non_blocking=True)
 
     e2e_step()
@@ -445,7 +452,8 @@ def main():
                        "parallelism": (f"round-robin brick-layer z-shards x{world}" if interleaved else f"z-slab x{world}") if world > 1 else "single GPU",
                        "voxels_updated_per_frame": uf_total / F, **extras},
             "clocks": clocks,
-            "e2e": {"value": fps_e2e, "unit": UNIT, "h2d_bytes_per_step": F * H * W * 2 + F * 128, "d2h_bytes_per_step": F * 8},
+            "e2e": {"value": fps_e2e, "unit": UNIT, "h2d_bytes_per_step": F * H * W * 2 + F * 128, "d2h_bytes_per_step": F * 8 * world,
+                    "ingest": "one pinned host buffer" if world == 1 else f"sharded: each of the {world} ranks feeds 1/{world} of every chunk from its own pinned host memory, pieces all-gathered over NVLink"},
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "kernel": "brick_integrate_kernel", "achieved": ach, "peak": peak, "unit": "GB/s",
                          "frac": (ach / peak) if ach else None, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,

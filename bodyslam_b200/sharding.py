@@ -348,6 +348,97 @@ class ShardedTSDF:
                 free[k % 3] = torch.cuda.Event()
                 free[k % 3].record(main)
 
+    # ------------------------------------------------------------------ sharded ingest
+    @staticmethod
+    def ingest_pieces(F: int, world_size: int, chunk: int = 256):
+        """Frame ownership of `integrate_stream_sharded`: per chunk (f0, f1) the list of per-rank
+        frame ranges [(a_0, b_0), ..., (a_{N-1}, b_{N-1})] (contiguous, in rank order, covering the
+        chunk).  -> (chunks, pieces)."""
+        from .tsdf import DenseTSDFVolume
+
+        chunks = DenseTSDFVolume.stream_chunks(F, chunk - chunk % world_size if chunk >= world_size else chunk,
+                                               ramp=ShardedTSDF.stream_ramp(world_size, False), multiple_of=world_size)
+        pieces = [[(f0 + (f1 - f0) * r // world_size, f0 + (f1 - f0) * (r + 1) // world_size) for r in range(world_size)]
+                  for f0, f1 in chunks]
+        return chunks, pieces
+
+    @staticmethod
+    def ingest_share(F: int, rank: int, world_size: int, chunk: int = 256):
+        """indices of the frames rank `rank` feeds (ascending) -- what its host buffer must hold, in this order"""
+        _, pieces = ShardedTSDF.ingest_pieces(F, world_size, chunk)
+        return np.concatenate([np.arange(a, b) for pc in pieces for (a, b) in [pc[rank]]]) if F else np.zeros(0, np.int64)
+
+    def integrate_stream_sharded(self, depth_u16_share, intrinsic, extrinsics, depth_scale: float = 1000.0, depth_trunc: float = 3.0,
+                                 chunk: int = 256, update_counts=None):
+        """Streamed replay with SHARDED INGEST: every rank feeds 1/N of each chunk from its own host
+        (or device) memory over its own PCIe link -- `depth_u16_share` holds the frames
+        `ingest_share(F, rank, N, chunk)` in that order -- and the pieces are exchanged over NVLink
+        (NCCL all-gather, or one broadcast per piece when a chunk does not divide evenly), so that
+        no single host link carries the whole stream.  `extrinsics` [F,4,4] is given on every rank.
+        Same pipeline as `integrate_stream` (copy stream / NCCL stream / current stream), same result."""
+        import torch
+        import torch.distributed as dist
+
+        from .geometry import intrinsic_params, to_numpy
+
+        vol = self.tsdf
+        dev = vol.device
+        N, rank = self.world_size, self.rank
+        W, H = intrinsic_params(intrinsic)[:2]
+        E = np.asarray(to_numpy(extrinsics), dtype=np.float64).reshape(-1, 4, 4)
+        F = E.shape[0]
+        if N == 1:
+            return self.integrate_stream(depth_u16_share, intrinsic, E, 0, depth_scale, depth_trunc, chunk, update_counts)
+        if vol.color:
+            raise RuntimeError("integrate_stream_sharded: colour volumes are not streamed yet (use integrate_batch)")
+        chunks, pieces = self.ingest_pieces(F, N, chunk)
+        if depth_u16_share.shape[0] != sum(pc[rank][1] - pc[rank][0] for pc in pieces):
+            raise RuntimeError("integrate_stream_sharded: this rank's share does not match ingest_share(F, rank, world_size, chunk)")
+        n = max(f1 - f0 for f0, f1 in chunks)
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream(dev)
+            if getattr(self, "_copy_stream", None) is None:
+                self._copy_stream = torch.cuda.Stream(dev)
+            cs = self._copy_stream
+            stage = vol._staging(n, H, W, False, count=3)
+            free = vol._stage_free
+            if depth_u16_share.is_cuda:
+                cs.wait_stream(main)
+            offs = np.concatenate([[0], np.cumsum([pc[rank][1] - pc[rank][0] for pc in pieces])])
+
+            def issue(k):
+                f0, f1 = chunks[k]
+                u16 = stage[k % 3][0][:f1 - f0]
+                a, b = pieces[k][rank]
+                works = []
+                with torch.cuda.stream(cs):
+                    if free[k % 3] is not None:
+                        cs.wait_event(free[k % 3])
+                    if b > a:
+                        u16[a - f0:b - f0].copy_(depth_u16_share[offs[k]:offs[k + 1]], non_blocking=True)
+                    sizes = {q1 - q0 for q0, q1 in pieces[k]}
+                    u8 = u16.view(torch.uint8)                       # NCCL has no 16-bit integer type: ship bytes
+                    if len(sizes) == 1:                              # equal pieces: one in-place all-gather
+                        works.append(dist.all_gather_into_tensor(u8, u8[a - f0:b - f0], group=self.group, async_op=True))
+                    else:
+                        for q, (q0, q1) in enumerate(pieces[k]):
+                            if q1 > q0:
+                                works.append(dist.broadcast(u8[q0 - f0:q1 - f0], q, group=self.group, async_op=True))
+                return works
+
+            pending = {0: issue(0)}
+            if len(chunks) > 1:
+                pending[1] = issue(1)
+            for k, (f0, f1) in enumerate(chunks):
+                if k + 2 < len(chunks):
+                    pending[k + 2] = issue(k + 2)
+                for w in pending.pop(k):
+                    w.wait()                                         # current stream waits for chunk k
+                vol.integrate_u16_batch(stage[k % 3][0][:f1 - f0], None, intrinsic, E[f0:f1], depth_scale, depth_trunc,
+                                        scratch=stage[k % 3][1], update_counts=None if update_counts is None else update_counts[f0:f1])
+                free[k % 3] = torch.cuda.Event()
+                free[k % 3].record(main)
+
     def build_3D_map(self, rgbd, intrinsic, extrinsic):
         self.tsdf.integrate(rgbd, intrinsic, extrinsic)
 

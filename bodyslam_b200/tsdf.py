@@ -201,11 +201,14 @@ class DenseTSDFVolume:
         return scratch
 
     @staticmethod
-    def stream_chunks(F: int, chunk: int = 256, ramp=(32, 64, 128)):
+    def stream_chunks(F: int, chunk: int = 256, ramp=(32, 64, 128), multiple_of: int = 1):
         """[(f0, f1)] for streamed integration: a short ramp first, so that the compute stream starts
-        after a 32-frame copy instead of a full chunk, then near-equal chunks of at most `chunk`."""
+        after a 32-frame copy instead of a full chunk, then near-equal chunks of at most `chunk`.
+        multiple_of: chunk sizes (except the last) are multiples of it (even split over N ranks)."""
         out, f = [], 0
+        q = max(1, int(multiple_of))
         for r in ramp:
+            r = -(-r // q) * q
             if F - f <= chunk or r >= chunk:
                 break
             out.append((f, f + r))
@@ -213,11 +216,13 @@ class DenseTSDFVolume:
         rest = F - f
         if rest > 0:
             n = -(-rest // chunk)
-            base, extra = divmod(rest, n)
+            units = -(-rest // q)                      # units of q frames, spread over n chunks
+            base, extra = divmod(units, n)
             for i in range(n):
-                m = base + (1 if i < extra else 0)
-                out.append((f, f + m))
-                f += m
+                m = min((base + (1 if i < extra else 0)) * q, F - f)
+                if m > 0:
+                    out.append((f, f + m))
+                    f += m
         return out
 
     def _staging(self, n, H, W, use_color, count=2):

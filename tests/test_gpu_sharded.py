@@ -43,6 +43,18 @@ def _worker(rank, world, port, ret, layout):
                              update_counts=counts)
         same = torch.equal(sh2.tsdf.export_dense()[0], sh.tsdf.export_dense()[0]) and torch.equal(sh2.tsdf.export_dense()[1], sh.tsdf.export_dense()[1])
         dist.all_reduce(counts)
+        # sharded ingest: every rank feeds its share of each chunk from its own pinned host memory
+        sh3 = ShardedTSDF(sc["voxel_length"], sc["sdf_trunc"], 128, sc["origin"], color=False, device=dev, rank=rank, world_size=world, layout=layout)
+        mine = ShardedTSDF.ingest_share(F, rank, world, 4)
+        sh3.integrate_stream_sharded(torch.from_numpy(sc["depth_u16"][mine]).pin_memory(), sc["intrinsic"], sc["E"], chunk=4)
+        same = same and torch.equal(sh3.tsdf.export_dense()[0], sh.tsdf.export_dense()[0]) and torch.equal(sh3.tsdf.export_dense()[1], sh.tsdf.export_dense()[1])
+        # an odd frame count leaves a last chunk that does not divide evenly: per-piece broadcasts, device-resident shares
+        sh4 = ShardedTSDF(sc["voxel_length"], sc["sdf_trunc"], 128, sc["origin"], color=False, device=dev, rank=rank, world_size=world, layout=layout)
+        mine = ShardedTSDF.ingest_share(5, rank, world, 4)
+        sh4.integrate_stream_sharded(torch.from_numpy(sc["depth_u16"][mine]).to(dev), sc["intrinsic"], sc["E"][:5], chunk=4)
+        sh5 = ShardedTSDF(sc["voxel_length"], sc["sdf_trunc"], 128, sc["origin"], color=False, device=dev, rank=rank, world_size=world, layout=layout)
+        sh5.integrate_batch(depth[:5].clone(), None, sc["intrinsic"], E[:5], broadcast_from=0)
+        same = same and torch.equal(sh4.tsdf.export_dense()[0], sh5.tsdf.export_dense()[0]) and torch.equal(sh4.tsdf.export_dense()[1], sh5.tsdf.export_dense()[1])
         if rank == 0:
             ref = DenseTSDFVolume(sc["voxel_length"], sc["sdf_trunc"], 128, sc["origin"], color=False, device=dev)
             ref.integrate_batch(depth, None, sc["intrinsic"], sc["E"])
