@@ -141,3 +141,24 @@ def test_stream_chunks_cover_all_frames_in_order():
             assert all(0 < f1 - f0 <= chunk for f0, f1 in ch)
     assert D.stream_chunks(1000, 256, ramp=()) == [(0, 250), (250, 500), (500, 750), (750, 1000)]
     assert [b - a for a, b in D.stream_chunks(1000)][:3] == [32, 64, 128]
+
+
+def test_sharded_ingest_ownership_partitions_every_chunk():
+    """ShardedTSDF.ingest_pieces / ingest_share: every frame is fed by exactly one rank, pieces are
+    contiguous, in rank order and cover each chunk; chunk sizes divide evenly except possibly the last"""
+    from bodyslam_b200.sharding import ShardedTSDF as S
+    from bodyslam_b200.tsdf import DenseTSDFVolume as D
+
+    for F in (1, 5, 6, 40, 255, 256, 257, 1000, 5000):
+        for N in (2, 3, 4, 8):
+            chunks, pieces = S.ingest_pieces(F, N, 256)
+            assert chunks[0][0] == 0 and chunks[-1][1] == F and all(0 < b - a <= 256 for a, b in chunks)
+            for (f0, f1), pc in zip(chunks, pieces):
+                assert len(pc) == N and pc[0][0] == f0 and pc[-1][1] == f1
+                assert all(a[1] == b[0] for a, b in zip(pc, pc[1:])) and all(b >= a for a, b in pc)
+            assert all((b - a) % N == 0 for a, b in chunks[:-1])
+            shares = [S.ingest_share(F, r, N, 256) for r in range(N)]
+            assert np.array_equal(np.sort(np.concatenate(shares)), np.arange(F))
+            assert all(np.all(np.diff(s) > 0) for s in shares if len(s) > 1)
+    assert D.stream_chunks(1000, 256, multiple_of=8)[:3] == [(0, 32), (32, 96), (96, 224)]
+    assert S.stream_ramp(1, True) == () and S.stream_ramp(8, True) == (64,) and S.stream_ramp(8, False) == (32, 64, 128)

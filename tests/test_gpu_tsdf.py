@@ -363,3 +363,19 @@ def test_unit_activation_needs_an_aligned_box(cuda):
     # the drop-in falls back to the dense rule when the box cannot hold whole units
     assert not TSDF(voxel_length=0.004, sdf_trunc=0.02, resolution=72, device=cuda, color=False).tsdf.unit_activation
     assert TSDF(voxel_length=0.004, sdf_trunc=0.02, resolution=64, device=cuda, color=False).tsdf.unit_activation
+
+
+@pytest.mark.parametrize("scale,trunc", [(1000.0, 3.0), (256.0, 0.0), (999.5, 0.2), (5000.0, 3.0), (3.0, 1000.0)])
+def test_fused_depth_conversion_is_ieee_exact_for_any_scale(cuda, scale, trunc):
+    """the fused a4 pass divides through a precomputed reciprocal + residual correction only after the
+    device has checked all 65 536 quotients for that divisor against IEEE division"""
+    from bodyslam_b200 import ops
+    g = torch.Generator().manual_seed(int(scale))
+    u16 = torch.randint(0, 65536, (2, 48, 64), generator=g, dtype=torch.int32).to(torch.uint16)
+    u16[0, 0, :8] = torch.tensor([0, 1, 2, 999, 1000, 65535, 32768, 3000], dtype=torch.int32).to(torch.uint16)
+    intr = small_scene("laparoscopy512", res=32, frames=1, W=64, H=48, with_color=False)
+    vol = DenseTSDFVolume(intr["voxel_length"], intr["sdf_trunc"], 32, intr["origin"], color=False, device=cuda)
+    scratch = vol.integrate_u16_batch(u16.to(cuda), None, intr["intrinsic"], np.stack([intr["E"][0]] * 2), depth_scale=scale, depth_trunc=trunc)
+    ref = oracle.o3d.depth_from_u16(u16.numpy(), scale, trunc if trunc > 0 else 1e30)
+    assert np.array_equal(scratch.cpu().numpy(), ref)
+    assert torch.equal(scratch, ops.depth_from_u16(u16, scale, trunc, cuda))
