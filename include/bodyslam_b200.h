@@ -148,7 +148,9 @@ BSLAM_API int bslam_tsdf_copy(const bslam_volume *src, bslam_volume *dst, bslam_
  * Replaces `TSDF.build_3D_map(rgbd, intrinsic, extrinsic)` N/3DM/tsdf.py:14-22 (Open3D
  * integrate) for F frames in order (F = 1: the per-frame SLAM loop N/3DM/slam.py:117,179;
  * F > 1: the replay of `update_map_after_pg` N/3DM/slam_utils.py:124-135).
- * d_depth [F][H][W] f32 metres (0 = invalid); d_rgb optional [F][H][W][3] u8 (colour volumes);
+ * d_depth [F][H][W] f32 metres (0 = invalid); d_rgb optional [F][H][W][3] u8 (colour volumes; read
+ * through the aligned 32-bit words that hold a pixel's bytes, so up to 3 bytes either side of the
+ * buffer are touched -- inside the allocation granule of any CUDA allocator);
  * h_K = {fx,fy,cx,cy} f64 HOST; h_extrinsics [F][16] f64 HOST row-major world->camera.
  * zmarch: BSLAM_ZMARCH_BRICK (fast path) or BSLAM_ZMARCH_LITERAL (validation kernel).
  * d_update_counts: optional DEVICE [F] u64, += number of voxels updated per frame.

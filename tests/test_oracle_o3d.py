@@ -133,3 +133,60 @@ def test_weight_zero_corner_suppresses_cubes():
     w[3, 3, 3] = 0                                               # kills the 4 cubes touching it in the crossing layer
     holed = V.extract_mesh()
     assert len(holed["triangles"]) == 2 * ((n - 1) ** 2 - 4)
+
+
+def test_scalable_units_follow_the_sampled_points_closed_form():
+    """orc_scalable_integrate (ScalableTSDFVolume, A.3 step 7): a fronto-parallel plane at depth d seen with
+    identity pose activates exactly the units hit by floor((p -+ trunc) / unit_len) of the stride-8 points,
+    leaves every other voxel at weight 0, and inside activated units equals the dense rule up to the
+    per-unit evaluation of the voxel centres."""
+    n, vl, trunc, d = 128, 0.002, 0.01, 0.15           # unit_len = 0.064, box = [-0.128, 0.128]^2 x [0, 0.256]
+    org = (-0.128, -0.128, 0.0)
+    V = oracle.o3d.Volume(n, vl, trunc, origin=org)
+    D = oracle.o3d.Volume(n, vl, trunc, origin=org)
+    upd, touched = V.integrate_scalable(plane_depth(d), K, np.eye(4), return_touched=True)
+    D.integrate(plane_depth(d), K, np.eye(4))
+    fx, fy, cx, cy = K
+    ul = vl * 32
+    want = np.zeros((4, 4, 4), bool)
+    for i in range(0, 480, 8):
+        for j in range(0, 640, 8):
+            p = np.array([(j - cx) * d / fx, (i - cy) * d / fy, d])
+            lo = np.floor((p - trunc) / ul).astype(int) - np.rint(np.array(org) / ul).astype(int)
+            hi = np.floor((p + trunc) / ul).astype(int) - np.rint(np.array(org) / ul).astype(int)
+            lo, hi = np.maximum(lo, 0), np.minimum(hi, 3)
+            if np.all(lo <= hi):
+                want[lo[0]:hi[0] + 1, lo[1]:hi[1] + 1, lo[2]:hi[2] + 1] = True
+    assert np.array_equal(touched.astype(bool), want)
+    assert want.sum() < want.size                      # the free space in front of the plane stays closed
+    w = V.grid("weight")
+    unit_of = lambda a: np.repeat(np.repeat(np.repeat(a, 32, 0), 32, 1), 32, 2)
+    assert not w[~unit_of(want)].any()                 # un-activated units are never written
+    assert upd == int((w > 0).sum())
+    # inside the activated units: same voxels as the dense rule (the plane is far from any pixel border here)
+    same_set = (w > 0) == ((D.grid("weight") > 0) & unit_of(want))
+    assert same_set.mean() > 0.9999
+    both = (w > 0) & (D.grid("weight") > 0)
+    assert np.abs(V.grid("tsdf")[both] - D.grid("tsdf")[both]).max() < 2e-3
+
+
+def test_scalable_needs_whole_units_on_the_world_grid():
+    V = oracle.o3d.Volume(72, 0.004, 0.02, origin=(-0.144,) * 3)
+    with pytest.raises(ValueError):
+        V.integrate_scalable(plane_depth(0.1), K, np.eye(4))
+    V = oracle.o3d.Volume(64, 0.004, 0.02, origin=(-0.1,) * 3)
+    with pytest.raises(ValueError):
+        V.integrate_scalable(plane_depth(0.1), K, np.eye(4))
+
+
+def test_cofactor_inverse_matches_lapack():
+    import ctypes as C
+    rng = np.random.default_rng(3)
+    for _ in range(20):
+        q, _r = np.linalg.qr(rng.normal(size=(3, 3)))
+        E = np.eye(4)
+        E[:3, :3] = q * np.sign(np.linalg.det(q))
+        E[:3, 3] = rng.normal(size=3)
+        out = np.zeros(16)
+        oracle.o3d.lib().orc_invert4x4(E.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+        assert np.abs(out.reshape(4, 4) - np.linalg.inv(E)).max() < 1e-14
