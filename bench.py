@@ -148,7 +148,7 @@ def workload_name(F, W, H, res, vl, trunc):
             f"sdf_trunc {trunc * 1e3:g} mm (BASELINE configs[3])")
 
 
-def cpu_sample(cfg, E, depth_u16_np, frame_ids, res, vl, trunc, budget_s=12.0, max_frames=24):
+def cpu_sample(cfg, E, depth_u16_np, frame_ids, res, vl, trunc, budget_s=10.0, max_frames=400):
     """time the oracle (Open3D-equivalent dense integrate, all host threads) on sample frames"""
     import oracle
 
@@ -424,12 +424,14 @@ def main():
     # ---- CPU baseline (rank 0, N = 1): the oracle on a bounded sample of the same frames
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        ids = np.linspace(0, F - 1, 24).astype(int)
+        # ~10 s of CPU work: up to 400 frames spread evenly over the sweep (the loop stops at the time budget)
+        ids = np.unique(np.linspace(0, F - 1, min(F, 400)).astype(int))
+        ids = ids[np.random.default_rng(0).permutation(len(ids))]   # any prefix of the sample is spread over the sweep
         sample_np = depth_u16.view(torch.int16)[torch.as_tensor(ids, device=dev)].view(torch.uint16).cpu().numpy()
         cpu_fps, n_cpu, cpu_counts, cores = cpu_sample(cfg, E, sample_np, ids, res, vl, trunc)
         gpu_counts = uf.cpu().numpy()[ids[:n_cpu]].tolist()
         cpu = {"value": cpu_fps, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"{n_cpu} frames spread over the {F}-frame sweep, {res}^3 dense sweep per frame "
+               "sample": f"{n_cpu} frames drawn evenly (seeded shuffle, 10 s budget) from the {F}-frame sweep, {res}^3 dense sweep per frame "
                          f"(oracle/o3d_oracle.c, OpenMP over x like Open3D)",
                "update_counts_match_gpu": cpu_counts == gpu_counts}
 
