@@ -56,3 +56,21 @@ def test_minmax_and_median():
     n = oracle.mdem.minmax_u8(d)
     assert n.min() == 0 and n.max() == 255 and n.dtype == np.uint8
     assert oracle.mdem.compute_median_scale_factor(d * 2, d) == 2.0
+
+
+def test_oracle_output_is_pinned(golden_dir):
+    """the oracle's own tsdf / weight / colour grids, update counts and mesh sizes on seeded scenes equal the
+    committed pins (tests/golden/make_oracle_pins.py) -- every GPU parity test leans on the oracle, so it
+    must not drift unnoticed"""
+    import importlib.util
+    import json
+    import os
+
+    spec = importlib.util.spec_from_file_location("make_oracle_pins", os.path.join(golden_dir, "make_oracle_pins.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    want = json.load(open(os.path.join(golden_dir, "oracle_pins.json")))
+    got = mod.compute()
+    assert got.keys() == want.keys()
+    for k in want:
+        assert got[k] == want[k], k
