@@ -46,6 +46,9 @@ _SIGNATURES = {
     "bslam_selftest": (C.c_int, [C.c_ulonglong, C.c_uint, _p, _p]),
     "bslam_tsdf_profile": (C.c_int, [_p, C.c_int]),
     "bslam_tsdf_profile_read": (C.c_int, [_p, _p, _p]),
+    "bslam_tsdf_profile_read_stages": (C.c_int, [_p, _p, _p]),
+    "bslam_tsdf_set_clip_check": (C.c_int, [_p, C.c_int, C.c_int]),
+    "bslam_tsdf_clip_stats": (C.c_int, [_p, _p, C.c_int, _p]),
     "bslam_tsdf_export": (C.c_int, [_p, _p, _p, _p, _p]),
     "bslam_tsdf_import": (C.c_int, [_p, _p, _p, _p, _p]),
     "bslam_tsdf_export_plane": (C.c_int, [_p, C.c_int, _p, _p]),

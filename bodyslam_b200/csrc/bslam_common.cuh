@@ -33,7 +33,33 @@ void set_error(const char *fmt, ...);
 
 constexpr int kBrick = BSLAM_BRICK;                 // 8
 constexpr int kBrickVox = kBrick * kBrick * kBrick; // 512
-constexpr int kNumSMs = 148;                        // B200
+constexpr int kNumSMsB200 = 148;                    // B200 (compile-time sizing hints only)
+
+// SM count of `device` (cached per device, thread-safe: the cache entries are written once with the
+// same value); grids of the persistent kernels are sized from it, not from a constant.
+int num_sms(int device);
+int current_device_sms();
+
+// Every entry point that touches a volume runs on the volume's device and restores the caller's
+// current device on the way out (torch reads it through cudaGetDevice).
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; cudaGetLastError(); }
+        if (prev != device) ok = cudaSetDevice(device) == cudaSuccess; else prev = -1;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceGuard(const DeviceGuard &) = delete;
+    DeviceGuard &operator=(const DeviceGuard &) = delete;
+};
+#define BSLAM_DEVICE_GUARD(dev)                                              \
+    ::bslam::DeviceGuard device_guard__(dev);                               \
+    if (!device_guard__.ok) {                                               \
+        ::bslam::set_error("cudaSetDevice(%d) failed (%s:%d)", (int)(dev), __FILE__, __LINE__); \
+        cudaGetLastError();                                                 \
+        return BSLAM_E_CUDA;                                                \
+    }
 
 // Device view of a brick-ordered volume.  Brick b = (bz*nby + by)*nbx + bx holds 512 float2
 // {tsdf, weight}; in-brick index = lz*64 + lx*8 + ly  (a warp owns 32 consecutive (lx,ly)
@@ -97,8 +123,11 @@ struct bslam_volume {
     int batch; // frames per integrate launch (0 = default)
     int prof_enabled, prof_n;
     int zpw;                                  // z layers per integrate warp (0 = auto by shard size)
-    static constexpr int kProfPairs = 2048;   // integrate launches timed per bslam_tsdf_profile_read
-    cudaEvent_t prof_ev[2 * kProfPairs];
-    double prof_ms_accum;
+    int clip_stride;                          // dense mode: sampling stride of the out-of-box point count (0 = off)
+    int z_total;                              // planes of the whole grid when this box is a z-shard (clip check)
+    static constexpr int kProfPairs = 1024;   // integrate launches timed per bslam_tsdf_profile_read
+    static constexpr int kProfStages = 3;     // depth statistics (+ fused a4) | unit marks + culls + order | brick integrate
+    cudaEvent_t prof_ev[(kProfStages + 1) * kProfPairs];
+    double prof_ms_accum[kProfStages];
     long long prof_launches_accum;
 };

@@ -433,15 +433,15 @@ __global__ void __launch_bounds__(kBrickVox) points_brick_kernel(const VolView v
 // candidate list of the volume -> sc.list / sc.totals[2] (shared by marching cubes and point extraction)
 static int build_candidates(bslam_volume *vol, const McScratch &sc, int have_halo_hi, cudaStream_t st) {
     const int64_t nb = brick_count(vol->v);
-    mc_mark_kernel<<<kNumSMs * 4, 256, 0, st>>>(vol->v, have_halo_hi, sc);
+    mc_mark_kernel<<<num_sms(vol->device) * 4, 256, 0, st>>>(vol->v, have_halo_hi, sc);
     BSLAM_LAUNCH_CHECK();
     brick_scan_kernel<<<1, 1024, 0, st>>>(sc.cand, nullptr, sc.cbase, nullptr, nb, sc.totals + 2);
     BSLAM_LAUNCH_CHECK();
-    mc_list_kernel<<<kNumSMs * 4, 256, 0, st>>>(nb, sc);
+    mc_list_kernel<<<num_sms(vol->device) * 4, 256, 0, st>>>(nb, sc);
     BSLAM_LAUNCH_CHECK();
     return BSLAM_OK;
 }
-constexpr int kExtractGrid = kNumSMs * 3;   // persistent CTAs of 512 threads (3 resident per SM)
+#define kExtractGrid (num_sms(vol->device) * 3)   /* persistent CTAs of 512 threads (3 resident per SM) */
 
 static int ensure_mc_scratch(bslam_volume *vol) {
     const size_t nb = (size_t)brick_count(vol->v);
@@ -463,7 +463,7 @@ extern "C" {
 int bslam_mc_count(bslam_volume *vol, const float *d_halo_lo, const float *d_halo_hi, int64_t *h_counts, bslam_stream_t stream) {
     BSLAM_CHECK_ARG(vol && h_counts, "bslam_mc_count: NULL argument");
     BSLAM_CHECK_ARG(vol->v.zs == 1, "bslam_mc_count: interleaved slabs must be re-sharded to contiguous ones first");
-    BSLAM_CUDA(cudaSetDevice(vol->device));
+    BSLAM_DEVICE_GUARD(vol->device);
     int rc = ensure_mc_scratch(vol);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
@@ -488,7 +488,7 @@ int bslam_mc_emit(bslam_volume *vol, const float *d_halo_lo, const float *d_halo
                   int64_t cap_v, int32_t *d_tri, int64_t cap_t, bslam_stream_t stream) {
     BSLAM_CHECK_ARG(vol && vol->mc_scratch, "bslam_mc_emit: call bslam_mc_count first");
     BSLAM_CHECK_ARG((d_vertices || cap_v == 0) && (d_tri || cap_t == 0), "bslam_mc_emit: NULL output");
-    BSLAM_CUDA(cudaSetDevice(vol->device));
+    BSLAM_DEVICE_GUARD(vol->device);
     const int64_t nb = brick_count(vol->v);
     const McScratch sc = carve_mc(vol->mc_scratch, (size_t)nb);
     mc_brick_kernel<true><<<kExtractGrid, kBrickVox, 0, (cudaStream_t)stream>>>(vol->v, vol->voxel_length_d, (const float2 *)d_halo_lo, (const float2 *)d_halo_hi, sc,
@@ -500,7 +500,7 @@ int bslam_mc_emit(bslam_volume *vol, const float *d_halo_lo, const float *d_halo
 int bslam_points_count(bslam_volume *vol, int64_t *h_count, bslam_stream_t stream) {
     BSLAM_CHECK_ARG(vol && h_count, "bslam_points_count: NULL argument");
     BSLAM_CHECK_ARG(vol->v.gz0 == 0 && vol->v.zs == 1, "bslam_points_count: single-box volumes only (gz0 must be 0)");
-    BSLAM_CUDA(cudaSetDevice(vol->device));
+    BSLAM_DEVICE_GUARD(vol->device);
     int rc = ensure_mc_scratch(vol);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
@@ -522,7 +522,7 @@ int bslam_points_count(bslam_volume *vol, int64_t *h_count, bslam_stream_t strea
 int bslam_points_emit(bslam_volume *vol, float *d_points, float *d_normals, float *d_colors, int32_t *d_keys, int64_t cap, bslam_stream_t stream) {
     BSLAM_CHECK_ARG(vol && vol->mc_scratch, "bslam_points_emit: call bslam_points_count first");
     BSLAM_CHECK_ARG(d_points || cap == 0, "bslam_points_emit: NULL output");
-    BSLAM_CUDA(cudaSetDevice(vol->device));
+    BSLAM_DEVICE_GUARD(vol->device);
     const int64_t nb = brick_count(vol->v);
     const McScratch sc = carve_mc(vol->mc_scratch, (size_t)nb);
     points_brick_kernel<true><<<kExtractGrid, kBrickVox, 0, (cudaStream_t)stream>>>(vol->v, vol->voxel_length_d, sc, d_points, d_normals, d_colors,

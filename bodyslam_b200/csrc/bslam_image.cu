@@ -588,7 +588,7 @@ __global__ void __launch_bounds__(kBpThreads) bp_emit_kernel(const __grid_consta
 
 static int grid_for(int64_t work_items, int per_block) {
     int64_t g = (work_items + per_block - 1) / per_block;
-    const int64_t cap = (int64_t)kNumSMs * 16;
+    const int64_t cap = (int64_t)current_device_sms() * 16;
     if (g > cap) g = cap;
     if (g < 1) g = 1;
     return (int)g;

@@ -219,7 +219,11 @@ class ShardedTSDF:
     """
 
     def __init__(self, voxel_length=0.001, sdf_trunc=0.1, resolution=512, origin=None, color=True, device=None,
-                 rank=None, world_size=None, group=None, layout="interleaved"):
+                 rank=None, world_size=None, group=None, layout="interleaved", unit_activation=None):
+        """unit_activation: like `TSDF` -- True = ScalableTSDFVolume semantics (a frame integrates only the 32^3
+        units its sampled points activate), False = dense UniformTSDFVolume rule, None (default) = True when the
+        whole grid consists of whole units on the world unit grid.  Same default as `TSDF`, so the sharded map
+        equals the single-GPU drop-in's."""
         import torch.distributed as dist
 
         from .tsdf import DenseTSDFVolume
@@ -233,6 +237,9 @@ class ShardedTSDF:
         self.bounds = slab_bounds(self.nz, self.world_size)
         if origin is None:
             origin = tuple(-0.5 * n * voxel_length for n in resolution)
+        if unit_activation is None:
+            unit_activation = DenseTSDFVolume.unit_aligned(resolution, voxel_length, origin)
+        self.unit_activation = bool(unit_activation)
         self._args = dict(voxel_length=voxel_length, sdf_trunc=sdf_trunc, origin=origin, color=color, device=device)
         n_layers = self.nz // BRICK
         if self.world_size == 1 or self.nz % BRICK or n_layers % self.world_size:
@@ -240,11 +247,12 @@ class ShardedTSDF:
         self.layout = layout
         if layout == "interleaved":
             self.tsdf = DenseTSDFVolume(voxel_length, sdf_trunc, (self.nx, self.ny, self.nz // self.world_size), origin, color=color,
-                                        device=device, gz0=BRICK * self.rank, z_total=self.nz, z_interleave=self.world_size)
+                                        device=device, gz0=BRICK * self.rank, z_total=self.nz, z_interleave=self.world_size,
+                                        unit_activation=self.unit_activation)
         else:
             z0, z1 = self.bounds[self.rank]
             self.tsdf = DenseTSDFVolume(voxel_length, sdf_trunc, (self.nx, self.ny, z1 - z0), origin, color=color, device=device,
-                                        gz0=z0, z_total=self.nz)
+                                        gz0=z0, z_total=self.nz, unit_activation=self.unit_activation)
 
     def integrate_batch(self, depth, color, intrinsic, extrinsics, broadcast_from=None):
         if broadcast_from is not None and self.world_size > 1:
@@ -287,7 +295,7 @@ class ShardedTSDF:
         on_dev = bool(getattr(depth_u16, "is_cuda", False))
         if self.world_size == 1:
             chunks = vol.stream_chunks(F, chunk, ramp=self.stream_ramp(1, on_dev))
-            if depth_u16.is_cuda:
+            if on_dev:
                 for f0, f1 in chunks:
                     vol.integrate_u16_batch(depth_u16[f0:f1], None, intrinsic, E[f0:f1], depth_scale, depth_trunc,
                                             update_counts=None if update_counts is None else update_counts[f0:f1])
@@ -451,7 +459,7 @@ class ShardedTSDF:
         z0, z1 = self.bounds[self.rank]
         a = self._args
         slab = DenseTSDFVolume(a["voxel_length"], a["sdf_trunc"], (self.nx, self.ny, z1 - z0), a["origin"], color=a["color"],
-                               device=self.tsdf.device, gz0=z0, z_total=self.nz)
+                               device=self.tsdf.device, gz0=z0, z_total=self.nz, unit_activation=self.unit_activation)
         send, recv = reshard_plan(self.nz // BRICK, self.world_size, self.rank)
         src, dst = self.tsdf.storage_layers(), slab.storage_layers()
         for k in src:

@@ -237,7 +237,14 @@ class DenseTSDFVolume:
             self._stage_key = key
             # event per staging buffer: the compute stream is done with it.  Kept across calls, so the
             # first copies of the next replay overlap the tail of this one instead of waiting for it.
-            self._stage_free = [None] * count
+            # Fresh buffers start with an event recorded on the allocating (current) stream: the caching
+            # allocator may hand out a block whose previous user's kernels are still queued there, and
+            # the first side-stream copy / NCCL receive into it must wait for them.
+            self._stage_free = []
+            for _ in range(count):
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream(dev))
+                self._stage_free.append(ev)
         return self._stage
 
     def integrate_host(self, depth_u16, color, intrinsic, extrinsics, depth_scale: float = 1000.0, depth_trunc: float = 3.0,
@@ -328,6 +335,24 @@ class DenseTSDFVolume:
         _lib.check(self._L.bslam_tsdf_profile_read(self._h, C.byref(ms), C.byref(n)))
         return ms.value, n.value
 
+    def profile_read_stages(self):
+        """-> ({stage: accumulated ms}, launches) since profile(True): the timeline of the integrate launches"""
+        ms, n = (C.c_double * 3)(), C.c_longlong()
+        _lib.check(self._L.bslam_tsdf_profile_read_stages(self._h, ms, C.byref(n)))
+        return {"depth_stats_a4": ms[0], "marks_culls_order": ms[1], "brick_integrate": ms[2]}, n.value
+
+    def set_clip_check(self, sampling_stride: int = 8):
+        """dense mode: count the stride-sampled depth points of every integrated frame that fall outside the
+        box (unit-activation mode always does); 0 = off.  See `clip_stats`."""
+        _lib.check(self._L.bslam_tsdf_set_clip_check(self._h, int(sampling_stride), int(self.z_total)))
+
+    def clip_stats(self, reset: bool = False):
+        """The reference's volume is unbounded, this box is not: -> dict(points, outside, partly_outside) over the
+        sampled depth points of the frames integrated so far (synchronises)."""
+        out = (C.c_ulonglong * 3)()
+        _lib.check(self._L.bslam_tsdf_clip_stats(self._h, out, int(bool(reset)), _lib.stream_ptr(self.device)))
+        return {"points": int(out[0]), "outside": int(out[1]), "partly_outside": int(out[2])}
+
     # ------------------------------------------------------------------ dense views (parity / interchange)
     def export_dense(self, with_color: bool = False):
         """(tsdf, weight[, color]) as [nx,ny,nz] f32 CUDA tensors in Open3D order x*ny*nz + y*nz + z."""
@@ -411,6 +436,27 @@ class TSDF:
             unit_activation = DenseTSDFVolume.unit_aligned(res, voxel_length, org)
         self.tsdf = DenseTSDFVolume(voxel_length=voxel_length, sdf_trunc=sdf_trunc, resolution=resolution, origin=origin,
                                     color=color, device=device, unit_activation=bool(unit_activation))
+        if not unit_activation:
+            self.tsdf.set_clip_check(8)
+        self._clip_warned = 0.0
+
+    def clipped_fraction(self) -> float:
+        """share of the sampled depth points integrated so far that fell OUTSIDE the bounded box (the
+        reference's ScalableTSDFVolume is unbounded and would have kept them)"""
+        st = self.tsdf.clip_stats()
+        return st["outside"] / st["points"] if st["points"] else 0.0
+
+    def _warn_if_clipped(self):
+        import warnings
+
+        frac = self.clipped_fraction()
+        if frac > 0.01 and frac > 1.5 * self._clip_warned:
+            self._clip_warned = frac
+            lo = self.tsdf.origin
+            hi = lo + np.array([self.tsdf.nx, self.tsdf.ny, self.tsdf.z_total]) * self.tsdf.voxel_length
+            warnings.warn(f"TSDF: {100 * frac:.1f} % of the depth points integrated so far lie outside the volume box "
+                          f"[{lo[0]:.3f}, {hi[0]:.3f}] x [{lo[1]:.3f}, {hi[1]:.3f}] x [{lo[2]:.3f}, {hi[2]:.3f}] m and were dropped "
+                          f"(the reference's ScalableTSDFVolume is unbounded); pass resolution= / origin= to TSDF() to cover the scene")
 
     def build_3D_map(self, rgbd, intrinsic, extrinsic):
         '''
@@ -430,13 +476,15 @@ class TSDF:
     def save_pcd(self, saving_path: str):
         from .io import write_point_cloud
 
-        pcd = self.tsdf.extract_point_cloud()
+        pcd = self.extract_pcd()
         write_point_cloud(saving_path, pcd)
 
     def extract_pcd(self):
+        self._warn_if_clipped()
         return self.tsdf.extract_point_cloud()
 
     def extract_mesh(self) -> TriangleMesh:
+        self._warn_if_clipped()
         return self.tsdf.extract_triangle_mesh()
 
     def save_mesh(self, saving_path: str):

@@ -46,7 +46,8 @@ enum {
 #define BSLAM_MAX_BATCH 256
 
 /* z-march modes of bslam_tsdf_integrate (see DESIGN.md "float32 recurrence") */
-#define BSLAM_ZMARCH_BRICK 8   /* camera-space point re-evaluated at every brick base (oracle z_restart=8) */
+#define BSLAM_ZMARCH_BRICK 8   /* camera-space point re-evaluated at every brick base (oracle z_restart=8); in unit-activation
+                                  mode at every UNIT base instead = Open3D's literal per-unit recurrence (oracle z_restart=0) */
 #define BSLAM_ZMARCH_LITERAL 0 /* Open3D's literal per-column float32 recurrence from z=0 (validation kernel) */
 
 BSLAM_API const char *bslam_last_error(void);
@@ -200,6 +201,16 @@ BSLAM_API int bslam_tsdf_set_batch(bslam_volume *vol, int frames_per_launch);
  */
 BSLAM_API int bslam_tsdf_set_unit_activation(bslam_volume *vol, int unit_resolution, int depth_sampling_stride, int z_total);
 
+/* The reference's ScalableTSDFVolume is unbounded; this box is not.  Every integrated frame's
+ * stride-sampled depth points (the same sampling ScalableTSDFVolume::Integrate uses) are
+ * back-projected and counted: h_stat3 = {points seen, points whose +-sdf_trunc neighbourhood lies
+ * entirely outside the box, points partly outside}.  Always on in unit-activation mode; in dense
+ * mode bslam_tsdf_set_clip_check(vol, stride > 0, z_total) turns it on (one extra small kernel per
+ * launch; z_total = planes of the whole grid when this box is a z-shard, 0 = gz0 + nz).
+ * bslam_tsdf_clip_stats synchronises the stream. */
+BSLAM_API int bslam_tsdf_set_clip_check(bslam_volume *vol, int sampling_stride, int z_total);
+BSLAM_API int bslam_tsdf_clip_stats(bslam_volume *vol, unsigned long long *h_stat3, int reset, bslam_stream_t stream);
+
 /* Chain-length histogram of the last integrate launch: h_hist32[k] = active bricks with 8k+1 .. 8k+8
  * active frames (measurement aid; synchronises). */
 BSLAM_API int bslam_tsdf_chain_histogram(bslam_volume *vol, unsigned int *h_hist32, bslam_stream_t stream);
@@ -221,11 +232,14 @@ BSLAM_API int bslam_selftest(unsigned long long n, unsigned int seed, unsigned l
                              bslam_stream_t stream);
 
 /* Measurement hook (bench.py roofline): when enabled, the dominant kernel of every integrate
- * launch (brick_integrate_kernel) is bracketed by CUDA events on the launch stream.  Up to 64
+ * launch (brick_integrate_kernel) is bracketed by CUDA events on the launch stream.  Up to 1024
  * launches are buffered between reads; bslam_tsdf_profile_read synchronises on them and returns
  * the accumulated kernel milliseconds and launch count since bslam_tsdf_profile(vol, 1). */
 BSLAM_API int bslam_tsdf_profile(bslam_volume *vol, int enable);
 BSLAM_API int bslam_tsdf_profile_read(bslam_volume *vol, double *h_ms_total, long long *h_launches);
+/* the same events, per stage of a launch: h_ms_stage3 = {depth statistics (+ fused a4), unit marks + culls + claim
+ * order, brick_integrate_kernel} accumulated milliseconds (the timeline of one integrate launch) */
+BSLAM_API int bslam_tsdf_profile_read_stages(bslam_volume *vol, double *h_ms_stage3, long long *h_launches);
 
 /* brick order <-> Open3D order idx = (x*ny + y)*nz + z (parity / interchange).
  * d_color: [nx*ny*nz*3] f32 or NULL. */

@@ -115,9 +115,10 @@ class Volume:
                                         self.nx, self.ny, self.nz, self.gz0, self.voxel_length, self.sdf_trunc,
                                         _ptr(self.origin), _ptr(d), _ptr(c), W, H, _ptr(Kd), _ptr(E), int(z_restart))
 
-    def integrate_scalable(self, depth_f32, K, extrinsic, rgb=None, z_restart=8, unit_res=32, stride=8, return_touched=False):
+    def integrate_scalable(self, depth_f32, K, extrinsic, rgb=None, z_restart=0, unit_res=32, stride=8, return_touched=False):
         """ScalableTSDFVolume.integrate (A.3 step 7; what `TSDF()` of N/3DM/tsdf.py:7-12 builds) on this dense
-        box, which must consist of whole units aligned to the world unit grid (origin = k * unit_length)."""
+        box, which must consist of whole units aligned to the world unit grid (origin = k * unit_length).
+        z_restart = 0 (default): Open3D's literal float32 recurrence inside every unit, from the unit's z = 0."""
         d = np.ascontiguousarray(depth_f32, dtype=np.float32)
         H, W = d.shape
         Kd = np.ascontiguousarray(K, dtype=np.float64)

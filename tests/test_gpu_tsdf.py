@@ -379,3 +379,132 @@ def test_fused_depth_conversion_is_ieee_exact_for_any_scale(cuda, scale, trunc):
     ref = oracle.o3d.depth_from_u16(u16.numpy(), scale, trunc if trunc > 0 else 1e30)
     assert np.array_equal(scratch.cpu().numpy(), ref)
     assert torch.equal(scratch, ops.depth_from_u16(u16, scale, trunc, cuda))
+
+
+def test_unit_mode_is_literal_open3d_per_unit_recurrence_on_interleaved_shards(cuda):
+    """unit-activation mode restarts the float32 z recurrence at every UNIT base (Open3D's per-unit
+    UniformTSDFVolume starts it there): oracle z_restart = 0, zero deviation -- also when the volume is an
+    interleaved z-shard (brick layers of one unit live on different ranks) and for every z split"""
+    sc = small_scene("laparoscopy512", res=128, frames=5, with_color=False)
+    ul = sc["voxel_length"] * 32
+    origin = np.floor(sc["origin"] / ul + 0.5) * ul
+    V = oracle.o3d.Volume(128, sc["voxel_length"], sc["sdf_trunc"], origin)
+    V8 = oracle.o3d.Volume(128, sc["voxel_length"], sc["sdf_trunc"], origin)
+    co = []
+    for i in range(5):
+        d = oracle.o3d.depth_from_u16(sc["depth_u16"][i])
+        co.append(V.integrate_scalable(d, sc["K"], sc["E"][i], z_restart=0))
+        V8.integrate_scalable(d, sc["K"], sc["E"][i], z_restart=8)
+    from bodyslam_b200 import ops
+    depth = ops.depth_from_u16(sc["depth_u16"], 1000.0, 3.0, cuda)
+    for zpw in (8, 4, 2):
+        vol = DenseTSDFVolume(sc["voxel_length"], sc["sdf_trunc"], 128, origin, color=False, device=cuda, unit_activation=True)
+        vol.set_z_split(zpw)
+        counts = torch.zeros(5, dtype=torch.int64, device=cuda)
+        vol.integrate_batch(depth, None, sc["intrinsic"], sc["E"], update_counts=counts)
+        assert counts.cpu().tolist() == co
+        assert_volume_equal(vol, V, sc["sdf_trunc"])
+    # 4 interleaved shards (rank r owns brick layers r, r + 4, ...): their union equals the literal oracle
+    tf, wf = (x.cpu().numpy() for x in vol.export_dense())
+    for r in range(4):
+        sh = DenseTSDFVolume(sc["voxel_length"], sc["sdf_trunc"], (128, 128, 32), origin, color=False, device=cuda, gz0=8 * r, z_total=128,
+                             z_interleave=4, unit_activation=True)
+        sh.integrate_batch(depth, None, sc["intrinsic"], sc["E"])
+        ts, ws = (x.cpu().numpy() for x in sh.export_dense())
+        for l in range(4):
+            g = (l * 4 + r) * 8
+            assert np.array_equal(ws[:, :, l * 8:l * 8 + 8], V.grid("weight")[:, :, g:g + 8])
+            assert np.array_equal(ts[:, :, l * 8:l * 8 + 8], V.grid("tsdf")[:, :, g:g + 8])
+    assert np.array_equal(wf, V.grid("weight")) and np.array_equal(tf, V.grid("tsdf"))
+
+
+def test_clip_statistics_and_warning_when_the_scene_leaves_the_box(cuda):
+    """the reference's ScalableTSDFVolume is unbounded, the box is not: dropped depth points are counted
+    (unit mode and dense mode) and the drop-in warns on extraction"""
+    sc = small_scene("laparoscopy512", res=64, frames=3, with_color=False)
+    from bodyslam_b200 import ops
+    depth = ops.depth_from_u16(sc["depth_u16"], 1000.0, 3.0, cuda)
+    n_pts = sum(int((oracle.o3d.depth_from_u16(sc["depth_u16"][i])[::8, ::8] > 0).sum()) for i in range(3))
+    for unit in (False, True):
+        # a 0.256 m cube around the origin: the cavity wall (> 0.2 m away) lies outside
+        t = TSDF(voxel_length=0.004, sdf_trunc=0.02, resolution=64, origin=(-0.128,) * 3, device=cuda, color=False, unit_activation=unit)
+        assert t.tsdf.unit_activation == unit
+        for i in range(3):
+            t.build_3D_map(RGBDImage(None, depth[i]), sc["intrinsic"], sc["E"][i])
+        st = t.tsdf.clip_stats()
+        assert st["points"] == n_pts and st["outside"] > 0.9 * n_pts, st
+        with pytest.warns(UserWarning, match="outside the volume box"):
+            t.extract_mesh()
+        # a box that covers the scene drops nothing and stays silent
+        ul = sc["voxel_length"] * 32
+        t = TSDF(voxel_length=sc["voxel_length"], sdf_trunc=sc["sdf_trunc"], resolution=64, origin=np.floor(sc["origin"] / ul + 0.5) * ul,
+                 device=cuda, color=False, unit_activation=unit)
+        for i in range(3):
+            t.build_3D_map(RGBDImage(None, depth[i]), sc["intrinsic"], sc["E"][i])
+        st = t.tsdf.clip_stats()
+        assert st["points"] == n_pts and st["outside"] == 0
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("error")
+            assert t.extract_mesh().triangles.shape[0] > 0
+
+
+def test_sharded_front_end_on_one_gpu_equals_the_drop_in(cuda):
+    """ShardedTSDF(world_size=1) takes numpy / host / device u16 frames and has TSDF()'s unit-activation default"""
+    from bodyslam_b200.sharding import ShardedTSDF
+    sc = small_scene("laparoscopy512", res=64, frames=4, with_color=False)
+    ul = sc["voxel_length"] * 32
+    origin = np.floor(sc["origin"] / ul + 0.5) * ul
+    ref = TSDF(voxel_length=sc["voxel_length"], sdf_trunc=sc["sdf_trunc"], resolution=64, origin=origin, device=cuda, color=False)
+    assert ref.tsdf.unit_activation
+    from bodyslam_b200 import ops
+    depth = ops.depth_from_u16(sc["depth_u16"], 1000.0, 3.0, cuda)
+    for i in range(4):
+        ref.build_3D_map(RGBDImage(None, depth[i]), sc["intrinsic"], sc["E"][i])
+    for src in (sc["depth_u16"], torch.from_numpy(sc["depth_u16"]), torch.from_numpy(sc["depth_u16"]).to(cuda)):
+        sh = ShardedTSDF(sc["voxel_length"], sc["sdf_trunc"], 64, origin, color=False, device=cuda, rank=0, world_size=1)
+        assert sh.unit_activation and sh.tsdf.unit_activation
+        sh.integrate_stream(src, sc["intrinsic"], sc["E"])
+        for x, y in zip(sh.tsdf.export_dense(), ref.tsdf.export_dense()):
+            assert torch.equal(x, y)
+
+
+def test_stage_profile_reports_every_stage(cuda):
+    sc = small_scene("laparoscopy512", res=64, frames=4, with_color=False)
+    vol = DenseTSDFVolume(sc["voxel_length"], sc["sdf_trunc"], 64, sc["origin"], color=False, device=cuda)
+    vol.profile(True)
+    vol.integrate_u16_batch(torch.from_numpy(sc["depth_u16"]).to(cuda), None, sc["intrinsic"], sc["E"])
+    stages, n = vol.profile_read_stages()
+    ms, n2 = vol.profile_read()
+    assert n == n2 == 1 and set(stages) == {"depth_stats_a4", "marks_culls_order", "brick_integrate"}
+    assert all(v > 0 for v in stages.values()) and abs(ms - stages["brick_integrate"]) < 1e-9
+
+
+@pytest.mark.slow
+def test_config1_colonoscopy_256_full_size_values(cuda):
+    """BASELINE configs[1] at FULL size: 300 frames, 640x480 -> 256^3 @ 2 mm; tsdf / weight VALUES (not counts)
+    bit-exact against the oracle (dense rule, z_restart 8) and against the literal per-unit oracle in
+    unit-activation mode; mesh vertex / triangle counts equal"""
+    from bodyslam_b200 import synthetic as S
+    from bodyslam_b200.geometry import PinholeCameraIntrinsic
+    cfg = S.config("colonoscopy256")
+    E = cfg["extrinsics"](300)
+    depth_u16, _ = S.render(cfg["surface"], E, K=cfg["K"], W=640, H=480, device=cuda, with_color=False)
+    intr = PinholeCameraIntrinsic(640, 480, *cfg["K"])
+    d_np = depth_u16.cpu().numpy()
+    ul = cfg["voxel_length"] * 32
+    org_u = np.floor(np.asarray(cfg["origin"]) / ul + 0.5) * ul
+    for unit, origin in ((False, np.asarray(cfg["origin"], dtype=np.float64)), (True, org_u)):
+        vol = DenseTSDFVolume(cfg["voxel_length"], cfg["sdf_trunc"], 256, origin, color=False, device=cuda, unit_activation=unit)
+        counts = torch.zeros(300, dtype=torch.int64, device=cuda)
+        vol.integrate_u16_batch(depth_u16, None, intr, E, update_counts=counts)
+        V = oracle.o3d.Volume(256, cfg["voxel_length"], cfg["sdf_trunc"], origin)
+        co = []
+        for i in range(300):
+            d = oracle.o3d.depth_from_u16(d_np[i])
+            co.append(V.integrate_scalable(d, cfg["K"], E[i]) if unit else V.integrate(d, cfg["K"], E[i]))
+        assert counts.cpu().tolist() == co
+        assert_volume_equal(vol, V, cfg["sdf_trunc"])
+        mesh, ref = vol.extract_triangle_mesh(), V.extract_mesh()
+        assert int(mesh.vertices.shape[0]) == len(ref["vertices"]) and int(mesh.triangles.shape[0]) == len(ref["triangles"])
+        assert len(ref["triangles"]) > 10000
