@@ -115,6 +115,35 @@ class TriangleMesh(_LazyArrays):
     def has_vertex_colors(self):
         return self.vertex_colors is not None
 
+    def canonical(self, dims):
+        """Order-independent form (numpy): (edge codes sorted, vertices in that order, triangles as rows of
+        ranks rotated to start at their smallest id and sorted) -- equal meshes give equal arrays whatever
+        order the vertices / triangles were emitted in (single GPU, z-slabs, the oracle's serial scan)."""
+        keys = to_numpy(self.vertex_keys).astype(np.int64)
+        verts = to_numpy(self.vertices)
+        tri = to_numpy(self.triangles).astype(np.int64)
+        nx, ny, nz = (int(d) for d in dims)
+        code = ((keys[:, 0] * (ny + 1) + keys[:, 1]) * (nz + 1) + keys[:, 2]) * 4 + keys[:, 3]
+        order = np.argsort(code, kind="stable")
+        rank = np.empty_like(order)
+        rank[order] = np.arange(len(order))
+        tri = rank[tri] if len(tri) else tri.reshape(0, 3)
+        if len(tri):
+            k = np.argmin(tri, axis=1)
+            tri = np.stack([np.take_along_axis(tri, ((k + i) % 3)[:, None], 1)[:, 0] for i in range(3)], 1)
+            tri = tri[np.lexsort((tri[:, 2], tri[:, 1], tri[:, 0]))]
+        return code[order], verts[order], tri
+
+    def canonical_digest(self, dims) -> str:
+        """sha256 over the canonical form (edge codes, vertex coordinates bit for bit, triangles)"""
+        import hashlib
+
+        code, verts, tri = self.canonical(dims)
+        h = hashlib.sha256()
+        for a in (code, np.ascontiguousarray(verts, dtype=np.float32), tri):
+            h.update(np.ascontiguousarray(a).tobytes())
+        return h.hexdigest()
+
 
 class PointCloud(_LazyArrays):
     """`.points`, `.colors`, `.normals` ([P,3] f32 each; colours/normals may be None)."""

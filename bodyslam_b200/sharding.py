@@ -458,8 +458,10 @@ class ShardedTSDF:
 
         z0, z1 = self.bounds[self.rank]
         a = self._args
-        slab = DenseTSDFVolume(a["voxel_length"], a["sdf_trunc"], (self.nx, self.ny, z1 - z0), a["origin"], color=a["color"],
-                               device=self.tsdf.device, gz0=z0, z_total=self.nz, unit_activation=self.unit_activation)
+        slab = getattr(self, "_slab", None)
+        if slab is None:      # kept across calls: every brick layer (voxels, colour, flags) is overwritten by the re-shard
+            slab = self._slab = DenseTSDFVolume(a["voxel_length"], a["sdf_trunc"], (self.nx, self.ny, z1 - z0), a["origin"], color=a["color"],
+                                                device=self.tsdf.device, gz0=z0, z_total=self.nz, unit_activation=self.unit_activation)
         send, recv = reshard_plan(self.nz // BRICK, self.world_size, self.rank)
         src, dst = self.tsdf.storage_layers(), slab.storage_layers()
         for k in src:

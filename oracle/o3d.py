@@ -34,6 +34,7 @@ def lib():
         L.orc_tsdf_integrate.argtypes = [p, p, p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
                                          p, p, p, C.c_int, C.c_int, p, p, C.c_int]
         L.orc_invert4x4.argtypes = [p, p]
+        L.orc_set_scalable_schedule.argtypes = [C.c_int]
         L.orc_scalable_integrate.restype = C.c_int64
         L.orc_scalable_integrate.argtypes = [p, p, p, C.c_int, C.c_int, C.c_int, p, C.c_int, C.c_int, C.c_double, C.c_double,
                                              p, p, C.c_int, C.c_int, p, p, p, C.c_int, p]
@@ -58,6 +59,12 @@ def num_threads() -> int:
 
 def set_num_threads(n: int) -> None:
     lib().orc_set_num_threads(int(n))
+
+
+def set_scalable_schedule(open3d_like: bool) -> None:
+    """threading of `Volume.integrate_scalable`: True = Open3D's own (touched units one after the other, OpenMP
+    only over the x loop inside a unit), False (default) = units spread over the threads (faster; same result)"""
+    lib().orc_set_scalable_schedule(0 if open3d_like else 1)
 
 
 def depth_from_u16(depth_u16, depth_scale=1000.0, depth_trunc=3.0):

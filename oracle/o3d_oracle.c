@@ -216,8 +216,15 @@ ORC_API void orc_invert4x4(const double *a, double *out) {
  *      origin = index * unit_length): A.3 steps 2-6 with x, y, z local to the unit.
  * z_restart as in orc_tsdf_integrate (applied to the unit-local z; unit_res is a multiple of 8).
  * touched_out: optional [nux*nuy*nuz] bytes ((ux*nuy + uy)*nuz + uz), 1 = integrated this frame.
+ * Threading follows g_scalable_schedule (orc_set_scalable_schedule): 0 = Open3D's own -- the touched
+ * units are integrated one after the other and only the x loop INSIDE a unit is an OpenMP
+ * `parallel for` (UniformTSDFVolume::IntegrateWithDepthToCameraDistanceMultiplier); 1 = the units
+ * themselves are spread over the threads (more parallel than the reference; same result).
  * Returns the number of voxels updated.
  */
+static int g_scalable_schedule = 1;
+ORC_API void orc_set_scalable_schedule(int s) { g_scalable_schedule = s; }
+
 ORC_API int64_t orc_scalable_integrate(float *tsdf, float *weight, float *color, int nx, int ny, int nz,
                                        const int *unit0, int unit_res, int stride, double voxel_length,
                                        double sdf_trunc, const float *depth, const uint8_t *rgb, int W, int H,
@@ -261,12 +268,14 @@ ORC_API int64_t orc_scalable_integrate(float *tsdf, float *weight, float *color,
     const float fxi = 1.0f / fx, fyi = 1.0f / fy;
     int64_t updated = 0;
     const int n_units = nux * nuy * nuz;
-#pragma omp parallel for schedule(dynamic) reduction(+ : updated)
+    const int par_units = g_scalable_schedule != 0;
+#pragma omp parallel for schedule(dynamic) reduction(+ : updated) if (par_units)
     for (int u = 0; u < n_units; ++u) {
         if (!touched[u]) continue;
         const int uz = u % nuz, uy = (u / nuz) % nuy, ux = u / (nuz * nuy);
         const double org[3] = {(double)(unit0[0] + ux) * unit_length, (double)(unit0[1] + uy) * unit_length,
                                (double)(unit0[2] + uz) * unit_length};
+#pragma omp parallel for schedule(static) reduction(+ : updated) if (!par_units)
         for (int x = 0; x < unit_res; ++x)
             for (int y = 0; y < unit_res; ++y) {
                 const float px = (float)((double)(half + vl * (float)x) + org[0]);
