@@ -504,6 +504,17 @@ def main():
                "ingest": "one pinned host buffer" if world == 1 else f"sharded: each of the {world} ranks feeds 1/{world} of every chunk from its own pinned host memory, pieces all-gathered over NVLink"}
         log(f"e2e: {fps_e2e:.1f} frames/s, {ms_e2e / args.steps:.2f} ms/step, mesh {nv} vertices / {nt} triangles")
         del mesh
+        if world > 1 and not args.no_mc:
+            prof = []
+            for _ in range(3):
+                barrier()
+                sh.extract_mesh(profile=True)
+                prof.append(sh.last_extract_profile)
+            mine_x = {k: float(np.median([p[k] for p in prof])) for k in prof[0]}
+            allx = [None] * world
+            dist.all_gather_object(allx, mine_x)
+            mesh_info["extract_mesh_phase_ms_max_over_ranks"] = {k: max(x[k] for x in allx) for k in mine_x}
+            log(f"multi-GPU extraction phases (ms, max over ranks, synchronised between phases): {json.dumps({k: round(v, 2) for k, v in mesh_info['extract_mesh_phase_ms_max_over_ranks'].items()})}")
     clocks = sampler.stop() if sampler else None   # samples inside both timed regions (resident + e2e)
 
     # ---- N > 1: the gathered mesh of one clean pass must equal the single-GPU mesh

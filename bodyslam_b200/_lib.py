@@ -23,6 +23,8 @@ _SIGNATURES = {
     "bslam_colorize_workspace_bytes": (C.c_size_t, [C.c_int]),
     "bslam_colorize": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_float, _p, _p, _p, C.c_double, C.c_double,
                                  C.c_int, C.c_uint16, C.c_uint32, _p, _p, _p, _p, _p]),
+    "bslam_colorize_f32_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "bslam_colorize_f32": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, _p, _p, C.c_double, C.c_double, C.c_int, C.c_float, C.c_uint32, _p, _p, _p, _p]),
     "bslam_minmax_u8": (C.c_int, [_p, C.c_int, C.c_int, C.c_int, _p, _p, _p, _p, _p]),
     "bslam_median_u16": (C.c_int, [_p, C.c_int, C.c_int64, C.c_int, C.c_uint16, _p, _p, _p]),
     "bslam_depth_from_u16": (C.c_int, [_p, C.c_int64, C.c_float, C.c_float, _p, _p]),
@@ -54,6 +56,8 @@ _SIGNATURES = {
     "bslam_tsdf_export_plane": (C.c_int, [_p, C.c_int, _p, _p]),
     "bslam_mc_count": (C.c_int, [_p, _p, _p, _p, _p]),
     "bslam_mc_emit": (C.c_int, [_p, _p, _p, _p, _p, _p, C.c_int64, _p, C.c_int64, _p]),
+    "bslam_mesh_merge_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "bslam_mesh_merge": (C.c_int, [C.c_int, _p, _p, _p, C.c_int, C.c_int, _p, _p, _p, _p, _p]),
     "bslam_points_count": (C.c_int, [_p, _p, _p]),
     "bslam_points_emit": (C.c_int, [_p, _p, _p, _p, _p, C.c_int64, _p]),
 }

@@ -443,6 +443,56 @@ static int build_candidates(bslam_volume *vol, const McScratch &sc, int have_hal
 }
 #define kExtractGrid (num_sms(vol->device) * 3)   /* persistent CTAs of 512 threads (3 resident per SM) */
 
+// ---------------------------------------------------------------- gather-side merge of per-slab meshes
+// The slabs' vertex keys / triangles are concatenated (bottom slab first).  Pass 1 (vertices): global z of
+// the key, and the vertices on every slab's plane 0 are entered into a per-slab table indexed by the edge code
+// (x * ny + y) * 4 + axis.  Pass 2 (triangle corners): local id -> + slab base; a negative id
+// -(1 + code) refers to the vertex on edge `code` of the NEXT slab's plane 0 (bslam_mc_emit) -> table.
+constexpr int kMaxSlabs = 64;
+struct MergeP {
+    int n;
+    long long vend[kMaxSlabs];   // exclusive end of slab s in the vertex array (vend[s-1] = its base)
+    long long tend[kMaxSlabs];
+    int zoff[kMaxSlabs];
+};
+
+__device__ __forceinline__ int slab_of(const long long *end, int n, long long i) {
+    int s = 0;
+    while (s < n - 1 && i >= end[s]) ++s;
+    return s;
+}
+
+__global__ void merge_vertices_kernel(const __grid_constant__ MergeP mp, int32_t *keys, long long nv, int ny, long long table_stride, int32_t *table) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nv) return;
+    const int s = slab_of(mp.vend, mp.n, i);
+    int4 k = reinterpret_cast<int4 *>(keys)[i];
+    if (k.z == 0) table[(long long)s * table_stride + ((long long)k.x * ny + k.y) * 4 + k.w] = (int32_t)i;
+    k.z += mp.zoff[s];
+    reinterpret_cast<int4 *>(keys)[i] = k;
+}
+
+__global__ void merge_triangles_kernel(const __grid_constant__ MergeP mp, int32_t *tris, long long nt, long long table_stride, const int32_t *table,
+                                       unsigned int *unresolved) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nt) return;
+    const int s = slab_of(mp.tend, mp.n, i);
+    const long long base = s ? mp.vend[s - 1] : 0;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const int32_t id = tris[3 * i + c];
+        int32_t out;
+        if (id >= 0) {
+            out = (int32_t)(id + base);
+        } else {
+            const long long code = -(long long)id - 1;
+            out = (s + 1 < mp.n && code < table_stride) ? table[(long long)(s + 1) * table_stride + code] : -1;
+            if (out < 0) atomicAdd(unresolved, 1u);
+        }
+        tris[3 * i + c] = out;
+    }
+}
+
 static int ensure_mc_scratch(bslam_volume *vol) {
     const size_t nb = (size_t)brick_count(vol->v);
     const size_t need = mc_scratch_bytes(nb);
@@ -494,6 +544,43 @@ int bslam_mc_emit(bslam_volume *vol, const float *d_halo_lo, const float *d_halo
     mc_brick_kernel<true><<<kExtractGrid, kBrickVox, 0, (cudaStream_t)stream>>>(vol->v, vol->voxel_length_d, (const float2 *)d_halo_lo, (const float2 *)d_halo_hi, sc,
                                                                                  d_vertices, d_keys, d_colors, cap_v, d_tri, cap_t);
     BSLAM_LAUNCH_CHECK();
+    return BSLAM_OK;
+}
+
+size_t bslam_mesh_merge_workspace_bytes(int n_slabs, int nx, int ny) {
+    if (n_slabs <= 0 || nx <= 0 || ny <= 0) return 0;
+    return (size_t)n_slabs * (size_t)nx * (size_t)ny * 4 * sizeof(int32_t) + 256;
+}
+
+int bslam_mesh_merge(int n_slabs, const int64_t *h_nv, const int64_t *h_nt, const int32_t *h_z_offsets, int nx, int ny, int32_t *d_keys,
+                     int32_t *d_tris, void *d_workspace, int64_t *h_unresolved, bslam_stream_t stream) {
+    BSLAM_CHECK_ARG(n_slabs >= 1 && n_slabs <= kMaxSlabs && h_nv && h_nt && h_z_offsets && d_workspace, "bslam_mesh_merge: bad argument (1..%d slabs)", kMaxSlabs);
+    BSLAM_CHECK_ARG(((uintptr_t)d_keys & 15) == 0, "bslam_mesh_merge: keys must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    MergeP mp;
+    memset(&mp, 0, sizeof(mp));
+    mp.n = n_slabs;
+    long long nv = 0, nt = 0;
+    for (int s = 0; s < n_slabs; ++s) {
+        nv += h_nv[s]; nt += h_nt[s];
+        mp.vend[s] = nv; mp.tend[s] = nt; mp.zoff[s] = h_z_offsets[s];
+    }
+    BSLAM_CHECK_ARG(nv < (1ll << 31), "bslam_mesh_merge: more than 2^31 vertices");
+    const long long stride = (long long)nx * ny * 4;
+    unsigned int *d_unres = (unsigned int *)d_workspace;
+    int32_t *table = (int32_t *)((char *)d_workspace + 256);
+    BSLAM_CUDA(cudaMemsetAsync(d_workspace, 0, 256, st));
+    BSLAM_CUDA(cudaMemsetAsync(table, 0xff, (size_t)n_slabs * stride * sizeof(int32_t), st));
+    if (nv) merge_vertices_kernel<<<(unsigned)((nv + 255) / 256), 256, 0, st>>>(mp, d_keys, nv, ny, stride, table);
+    BSLAM_LAUNCH_CHECK();
+    if (nt) merge_triangles_kernel<<<(unsigned)((nt + 255) / 256), 256, 0, st>>>(mp, d_tris, nt, stride, table, d_unres);
+    BSLAM_LAUNCH_CHECK();
+    if (h_unresolved) {
+        unsigned int u = 0;
+        BSLAM_CUDA(cudaMemcpyAsync(&u, d_unres, 4, cudaMemcpyDeviceToHost, st));
+        BSLAM_CUDA(cudaStreamSynchronize(st));
+        *h_unresolved = u;
+    }
     return BSLAM_OK;
 }
 

@@ -102,8 +102,10 @@ def colorize(value, vmin=None, vmax=None, cmap='gray_r', invalid_val=-99, invali
              background_color=(128, 128, 128, 255), gamma_corrected=False, value_transform=None):
     """Converts a depth map to a color image.  (reference signature, depth_map_scaling.py:12)
 
-    value: [H,W] (any singleton dims squeezed) integer-valued depth in [0, 65535] -- the uint16
-    image `np.array(PIL I;16)` the reference feeds it -- as numpy or torch (CPU/CUDA).
+    value: [H,W] (any singleton dims squeezed), numpy or torch (CPU/CUDA): the uint16 image
+    `np.array(PIL I;16)` the reference feeds it (any integer-valued depth in [0, 65535]), or a
+    float32 image of arbitrary values such as ZoeDepth's metres tensor (evaluated in NumPy's float32
+    arithmetic, exactly like the reference does for a float32 array).
     Returns a numpy [H,W,4] uint8 RGBA image like the reference.  Percentiles, normalisation,
     LUT indexing and painting all run on the GPU; the byte LUT (with gamma folded in) and, for
     `value_transform`, the 65536-entry index table are the only host-side preparation.
@@ -126,16 +128,29 @@ def colorize_cuda(value, vmin=None, vmax=None, cmap='gray_r', invalid_val=-99, i
         name = str(v.dtype)
     if name not in ("uint16", "uint8", "int16", "int32", "int64", "float32", "float64"):
         raise RuntimeError(f"[colorize] Unsupported image format. (dtype {name})")
-    if name != "uint16":
-        vn = to_numpy(v)
-        if vn.size and (vn.min() < 0 or vn.max() > 65535 or (name.startswith("float") and np.any(vn != np.floor(vn)))):
-            raise RuntimeError("[colorize] the CUDA path takes integer-valued depth in [0, 65535] (uint16 depth maps); "
-                               "scale float metres with scale_to_u16 first")
-        v = vn.astype(np.uint16)
     lut = get_cmap_lut(cmap)
     bg = np.asarray(list(background_color) + [255] * (4 - len(background_color)), dtype=np.uint8)
     if gamma_corrected:
         lut, bg = _gamma_u8(lut), _gamma_u8(bg)
+    if name == "float32":
+        # float metres (a ZoeDepth tensor, depth_map_scaling.py:14-15): NumPy's float32 arithmetic, exact radix select
+        if value_transform is not None:
+            raise RuntimeError("[colorize] value_transform is only supported for integer-valued (uint16) depth on the CUDA path")
+        vt = ops.as_cuda(v, torch.float32, device)
+        inv = invalid_val
+        if invalid_mask is not None:
+            m = ops.as_cuda(invalid_mask, torch.bool, device).reshape(vt.shape)
+            inv = float(np.finfo(np.float32).min)
+            while bool((vt == inv).any()):
+                inv = float(np.nextafter(np.float32(inv), np.float32(0)))
+            vt = torch.where(m, torch.full_like(vt, inv), vt)
+        return ops.colorize_f32(lut, vt, invalid_val=inv, background=bg, vmin=vmin, vmax=vmax, device=device)
+    if name != "uint16":
+        vn = to_numpy(v)
+        if vn.size and (vn.min() < 0 or vn.max() > 65535 or (name.startswith("float") and np.any(vn != np.floor(vn)))):
+            raise RuntimeError("[colorize] float64 / signed input must be integer-valued depth in [0, 65535] on the CUDA path "
+                               "(float32 images of any value are supported: pass value.astype(np.float32) / tensor.float())")
+        v = vn.astype(np.uint16)
     if invalid_mask is not None:
         # an explicit mask replaces `value == invalid_val` (depth_map_scaling.py:17-18): paint the
         # masked pixels with a sentinel value no valid pixel uses and hand that to the kernel

@@ -126,6 +126,41 @@ def colorize_u16(lut_rgba, depth_m=None, depth_u16=None, scale=256.0, invalid_va
     return (rgba, u16, stats) if return_stats else (rgba, u16)
 
 
+def colorize_f32(lut_rgba, value, invalid_val=None, background=(128, 128, 128, 255), vmin=None, vmax=None, p_lo=2.0, p_hi=85.0,
+                 device=None, return_stats=False):
+    """K1, float flavour: percentile-normalised colour mapping of a float32 [B,H,W] / [H,W] image in NumPy's
+    float32 arithmetic (the reference's `colorize` on a float tensor / array, depth_map_scaling.py:12-45).
+    Returns rgba [.., H, W, 4] u8 CUDA (and the per-image (vmin, vmax) f64 CUDA tensor with return_stats)."""
+    torch = _lib.require_cuda()
+    dev = _device(device)
+    L = _lib.load()
+    src = as_cuda(value, torch.float32, dev)
+    squeeze = src.dim() == 2
+    if squeeze:
+        src = src.unsqueeze(0)
+    if src.dim() != 3:
+        raise RuntimeError(f"[colorize] Unsupported image format. (shape {tuple(src.shape)})")
+    B, H, W = src.shape
+    lut = as_cuda(np.ascontiguousarray(to_numpy(lut_rgba), dtype=np.uint8).reshape(256, 4), torch.uint8, dev)
+    rgba = torch.empty((B, H, W, 4), dtype=torch.uint8, device=dev)
+    ws = torch.empty(L.bslam_colorize_f32_workspace_bytes(B), dtype=torch.uint8, device=dev)
+    stats = torch.empty((B, 2), dtype=torch.float64, device=dev)
+    h_over = None
+    if vmin is not None or vmax is not None:
+        h_over = np.full((B, 2), np.nan, np.float64)
+        if vmin is not None:
+            h_over[:, 0] = np.asarray(vmin, dtype=np.float64)
+        if vmax is not None:
+            h_over[:, 1] = np.asarray(vmax, dtype=np.float64)
+    with torch.cuda.device(dev):
+        _lib.check(L.bslam_colorize_f32(_lib.ptr(src), B, H, W, _lib.ptr(rgba), _lib.ptr(lut), float(p_lo), float(p_hi),
+                                        int(invalid_val is not None), float(invalid_val if invalid_val is not None else 0.0),
+                                        _pack_rgba(background), _lib.ptr(h_over), _lib.ptr(stats), _lib.ptr(ws), _lib.stream_ptr(dev)))
+    if squeeze:
+        rgba = rgba[0]
+    return (rgba, stats) if return_stats else rgba
+
+
 def minmax_colormap(depth_u16, lut_bgr=None, device=None):
     """a12: `np.uint8(255*(d-min)/(max-min))` (+ 3-byte LUT) of N/3DM/slam_utils.py:250-264."""
     torch = _lib.require_cuda()

@@ -41,43 +41,45 @@ def merge_slab_meshes(meshes, z_offsets, ny: int) -> TriangleMesh:
 
     Vertex ids are rebased by the running vertex count; a negative id -(1 + (x*ny + y)*4 + axis)
     refers to the vertex on edge (x, y, z=0, axis) of the NEXT slab and is resolved through that
-    slab's vertex keys.  Keys are returned with global z.  Works on torch tensors (any device).
+    slab's vertex keys.  Keys are returned with global z.  Works on torch tensors (any device); all
+    slabs are handled by one set of tensor operations (one sort + one binary search for the
+    cross-slab references, one host synchronisation for the consistency check).
     """
     import torch
 
     n = len(meshes)
-    bases, acc = [], 0
-    for m in meshes:
-        bases.append(acc)
-        acc += int(m.vertices.shape[0])
-    verts, keys, cols, tris = [], [], [], []
-    for i, m in enumerate(meshes):
-        k = m.vertex_keys.clone()
-        k[:, 2] += int(z_offsets[i])
-        verts.append(m.vertices)
-        keys.append(k)
-        if m.vertex_colors is not None:
-            cols.append(m.vertex_colors)
-        t = m.triangles.to(torch.int64).clone()
-        neg = t < 0
-        if bool(neg.any()):
-            if i + 1 >= n:
-                raise RuntimeError("merge_slab_meshes: the top slab references a slab above it")
-            nk = meshes[i + 1].vertex_keys.to(torch.int64)
-            plane0 = torch.nonzero(nk[:, 2] == 0).reshape(-1)
-            code = (nk[plane0, 0] * ny + nk[plane0, 1]) * 4 + nk[plane0, 3]
-            order = torch.argsort(code)
-            code_sorted = code[order]
-            want = -t[neg] - 1
-            pos = torch.searchsorted(code_sorted, want)
-            pos = pos.clamp_max(max(code_sorted.numel() - 1, 0))
-            if code_sorted.numel() == 0 or not bool((code_sorted[pos] == want).all()):
+    dev = meshes[0].vertices.device
+    nv = torch.tensor([int(m.vertices.shape[0]) for m in meshes], dtype=torch.int64)
+    nt = torch.tensor([int(m.triangles.shape[0]) for m in meshes], dtype=torch.int64)
+    base = torch.cumsum(nv, 0) - nv                                          # first global id of every slab
+    verts = torch.cat([m.vertices for m in meshes])
+    keys = torch.cat([m.vertex_keys for m in meshes]).clone()
+    slab_of_v = torch.repeat_interleave(torch.arange(n), nv).to(dev)
+    local_z0 = keys[:, 2] == 0
+    keys[:, 2] += torch.as_tensor(np.asarray(z_offsets, dtype=np.int64), device=dev)[slab_of_v].to(keys.dtype)
+    has_col = all(m.vertex_colors is not None for m in meshes) and n > 0
+    cols = torch.cat([m.vertex_colors for m in meshes]) if has_col else None
+    tris = torch.cat([m.triangles for m in meshes]).to(torch.int64)
+    slab_of_t = torch.repeat_interleave(torch.arange(n), nt).to(dev)
+    base_d = base.to(dev)
+    neg = tris < 0
+    out = tris + base_d[slab_of_t][:, None]
+    if int(nt.sum()) and int(nv.sum()):
+        # lookup table of the vertices on every slab's plane 0: (slab, edge code) -> global id
+        k64 = keys.to(torch.int64)
+        M = 4 * (int(ny) + 1) * (int(k64[:, 0].max().item()) + 2)              # > any edge code
+        p0 = torch.nonzero(local_z0).reshape(-1)
+        code = slab_of_v[p0] * M + (k64[p0, 0] * ny + k64[p0, 1]) * 4 + k64[p0, 3]
+        code_sorted, order = torch.sort(code)
+        want = (slab_of_t[:, None].expand(-1, 3)[neg] + 1) * M + (-tris[neg] - 1)
+        if want.numel():
+            if code_sorted.numel() == 0:
                 raise RuntimeError("merge_slab_meshes: unresolved cross-slab vertex reference")
-            t[neg] = plane0[order[pos]] + bases[i + 1]
-        t[~neg] += bases[i]
-        tris.append(t.to(torch.int32))
-    cat = lambda xs, shape, dt: torch.cat(xs) if xs else torch.empty(shape, dtype=dt)
-    return TriangleMesh(torch.cat(verts), torch.cat(tris), torch.cat(cols) if len(cols) == n and n else None, torch.cat(keys))
+            pos = torch.searchsorted(code_sorted, want).clamp_max(code_sorted.numel() - 1)
+            if not bool((code_sorted[pos] == want).all()):
+                raise RuntimeError("merge_slab_meshes: unresolved cross-slab vertex reference (or the top slab references a slab above it)")
+            out[neg] = p0[order[pos]]
+    return TriangleMesh(verts, out.to(torch.int32), cols, keys)
 
 
 def broadcast_frames(depth, color, extrinsics, src: int = 0, group=None):
@@ -121,44 +123,65 @@ def exchange_halo_planes(top_plane, bottom_plane, rank: int, world_size: int, gr
     return halo_lo, halo_hi
 
 
+def _pack_mesh(mesh: TriangleMesh):
+    """vertices f32 [V,3] | keys i32 [V,4] | triangles i32 [T,3] | colours f32 [V,3] as ONE int32 buffer"""
+    import torch
+
+    parts = [mesh.vertices.contiguous().view(torch.int32).reshape(-1), mesh.vertex_keys.contiguous().to(torch.int32).reshape(-1),
+             mesh.triangles.contiguous().to(torch.int32).reshape(-1)]
+    if mesh.vertex_colors is not None:
+        parts.append(mesh.vertex_colors.contiguous().view(torch.int32).reshape(-1))
+    return torch.cat(parts) if sum(p.numel() for p in parts) else torch.empty(0, dtype=torch.int32, device=mesh.vertices.device)
+
+
+def _unpack_mesh(buf, V: int, T: int, has_col: bool) -> TriangleMesh:
+    import torch
+
+    o = 0
+    verts = buf[o:o + 3 * V].view(torch.float32).view(V, 3); o += 3 * V
+    keys = buf[o:o + 4 * V].view(V, 4); o += 4 * V
+    tris = buf[o:o + 3 * T].view(T, 3); o += 3 * T
+    cols = buf[o:o + 3 * V].view(torch.float32).view(V, 3) if has_col else None
+    return TriangleMesh(verts, tris, cols, keys)
+
+
 def gather_meshes(mesh: TriangleMesh, rank: int, world_size: int, dst: int = 0, group=None):
-    """variable-size gather of per-rank meshes to `dst` -> list of TriangleMesh (None elsewhere)."""
+    """variable-size gather of per-rank meshes to `dst` -> list of TriangleMesh (None elsewhere).
+    One size exchange (all-gather of 3 integers) and ONE packed message per rank."""
     import torch
     import torch.distributed as dist
 
     dev = mesh.vertices.device
     has_col = mesh.vertex_colors is not None
     mine = torch.tensor([mesh.vertices.shape[0], mesh.triangles.shape[0], int(has_col)], dtype=torch.int64, device=dev)
-    sizes = [torch.zeros_like(mine) for _ in range(world_size)]
-    dist.all_gather(sizes, mine, group=group)
-    sizes = [s.tolist() for s in sizes]
+    sizes = torch.empty(world_size * 3, dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(sizes, mine, group=group)
+    sizes = sizes.view(world_size, 3).tolist()
+    words = lambda V, T, c: 7 * V + 3 * T + (3 * V if c else 0)
     if rank != dst:
-        ops_ = [dist.P2POp(dist.isend, mesh.vertices.contiguous(), dst, group),
-                dist.P2POp(dist.isend, mesh.vertex_keys.contiguous(), dst, group),
-                dist.P2POp(dist.isend, mesh.triangles.contiguous(), dst, group)]
-        if has_col:
-            ops_.append(dist.P2POp(dist.isend, mesh.vertex_colors.contiguous(), dst, group))
-        ops_ = [o for o in ops_ if o.tensor.numel() > 0]
-        if ops_:
-            for w in dist.batch_isend_irecv(ops_):
+        buf = _pack_mesh(mesh)
+        if buf.numel():    # batched like the receiving side: un-batched NCCL send / recv use a separate pair communicator
+            for w in dist.batch_isend_irecv([dist.P2POp(dist.isend, buf, dst, group)]):
                 w.wait()
         return None
-    out, ops_ = [], []
+    out, ops_, bufs = [], [], {}
     for r in range(world_size):
-        if r == dst:
-            out.append(mesh)
-            continue
         V, T, c = sizes[r]
-        m = TriangleMesh(torch.empty((V, 3), dtype=torch.float32, device=dev), torch.empty((T, 3), dtype=torch.int32, device=dev),
-                         torch.empty((V, 3), dtype=torch.float32, device=dev) if c else None,
-                         torch.empty((V, 4), dtype=torch.int32, device=dev))
-        for t in (m.vertices, m.vertex_keys, m.triangles, m.vertex_colors):
-            if t is not None and t.numel() > 0:
-                ops_.append(dist.P2POp(dist.irecv, t, r, group))
-        out.append(m)
+        if r != dst and words(V, T, c):
+            bufs[r] = torch.empty(words(V, T, c), dtype=torch.int32, device=dev)
+            ops_.append(dist.P2POp(dist.irecv, bufs[r], r, group))
     if ops_:
         for w in dist.batch_isend_irecv(ops_):
             w.wait()
+    for r in range(world_size):
+        V, T, c = sizes[r]
+        if r == dst:
+            out.append(mesh)
+        elif r in bufs:
+            out.append(_unpack_mesh(bufs[r], V, T, bool(c)))
+        else:
+            out.append(TriangleMesh(torch.empty((0, 3), dtype=torch.float32, device=dev), torch.empty((0, 3), dtype=torch.int32, device=dev),
+                                    torch.empty((0, 3), dtype=torch.float32, device=dev) if c else None, torch.empty((0, 4), dtype=torch.int32, device=dev)))
     return out
 
 
@@ -181,29 +204,25 @@ def reshard_plan(n_layers: int, world_size: int, rank: int):
 
 def reshard_layers(src_layers, dst_layers, send, recv, group=None):
     """all-to-all of whole brick layers: src_layers / dst_layers are [n_local_layers, bytes] uint8
-    views (interleaved source, contiguous destination)."""
+    views (interleaved source, contiguous destination).  The layers a rank sends to rank q are a
+    contiguous run of its local layers (ascending q = ascending local index), so the source view IS
+    the send buffer of one `all_to_all_single`; the received layers land in a staging buffer ordered
+    by source rank and one indexed copy scatters them (skipped when that order already is the slab's)."""
     import torch
     import torch.distributed as dist
 
     dev = src_layers.device
-    rank = dist.get_rank(group)
-    ins = [src_layers[torch.as_tensor(ix, dtype=torch.long, device=dev)].contiguous() for ix in send]
-    outs = [torch.empty((len(ix), src_layers.shape[1]), dtype=src_layers.dtype, device=dev) for ix in recv]
-    ops_ = []
-    for p in range(len(send)):     # point-to-point pairs (NCCL groups them; gloo has no all_to_all)
-        if p == rank:
-            outs[p].copy_(ins[p])
-            continue
-        if ins[p].numel():
-            ops_.append(dist.P2POp(dist.isend, ins[p], p, group))
-        if outs[p].numel():
-            ops_.append(dist.P2POp(dist.irecv, outs[p], p, group))
-    if ops_:
-        for w in dist.batch_isend_irecv(ops_):
-            w.wait()
-    for buf, ix in zip(outs, recv):
-        if ix:
-            dst_layers[torch.as_tensor(ix, dtype=torch.long, device=dev)] = buf
+    n_in = [len(ix) for ix in send]
+    n_out = [len(ix) for ix in recv]
+    flat_send = [l for ix in send for l in ix]
+    if flat_send != list(range(src_layers.shape[0])):
+        raise ValueError("reshard_layers: the send plan must cover the local layers in ascending order")
+    perm = [l for ix in recv for l in ix]
+    direct = perm == list(range(dst_layers.shape[0]))
+    out = dst_layers if direct else torch.empty_like(dst_layers)
+    dist.all_to_all_single(out, src_layers.contiguous(), output_split_sizes=n_out, input_split_sizes=n_in, group=group)
+    if not direct:
+        dst_layers.index_copy_(0, torch.as_tensor(perm, dtype=torch.long, device=dev), out)
 
 
 class ShardedTSDF:
@@ -468,14 +487,92 @@ class ShardedTSDF:
             reshard_layers(src[k], dst[k], send, recv, self.group)
         return slab
 
-    def extract_mesh(self):
-        """full mesh on rank 0 (None on the other ranks)"""
+    def extract_mesh(self, profile: bool = False):
+        """full mesh on rank 0 (None on the other ranks).  profile=True synchronises between the phases and leaves
+        their wall-clock milliseconds in `self.last_extract_profile` (measurement aid)."""
         if self.world_size == 1:
             return self.tsdf.extract_triangle_mesh()
+        import time
+
+        import torch
+
+        t = [time.perf_counter()]
+
+        def mark():
+            if profile:
+                torch.cuda.synchronize(self.tsdf.device)
+                t.append(time.perf_counter())
+
         v = self.contiguous_slab()
+        mark()
         lo, hi = exchange_halo_planes(v.export_plane(v.nz - 1), v.export_plane(0), self.rank, self.world_size, self.group)
-        mesh = v.extract_triangle_mesh(halo_lo=lo, halo_hi=hi)
-        parts = gather_meshes(mesh, self.rank, self.world_size, 0, self.group)
-        if parts is None:
+        mark()
+        out = self._gather_slab_meshes(v, lo, hi, profile_mark=mark)
+        if profile:
+            names = ("reshard_to_slabs", "halo_exchange", "marching_cubes_count", "sizes_allgather", "emit_and_gather", "merge")
+            self.last_extract_profile = {n: 1e3 * (b - a) for n, a, b in zip(names, t[:-1], t[1:])}
+        return out
+
+    def _gather_slab_meshes(self, v, lo, hi, profile_mark=lambda: None):
+        """count per slab -> sizes to everybody -> rank 0 allocates the WHOLE mesh once; every slab's marching cubes
+        emit straight into its rows (rank 0) or into a send buffer (others) and the pieces are received in place ->
+        two small kernels (bslam_mesh_merge) rebase the vertex ids and resolve the cross-slab references."""
+        import ctypes as C
+
+        import torch
+        import torch.distributed as dist
+
+        from . import _lib
+
+        dev, N, rank = v.device, self.world_size, self.rank
+        V, T = v.mc_count(lo, hi)
+        profile_mark()
+        sizes = torch.empty(N * 2, dtype=torch.int64, device=dev)
+        dist.all_gather_into_tensor(sizes, torch.tensor([V, T], dtype=torch.int64, device=dev), group=self.group)
+        sizes = sizes.view(N, 2).cpu().numpy()
+        profile_mark()
+        nv, nt = sizes[:, 0].copy(), sizes[:, 1].copy()
+        if rank != 0:
+            verts = torch.empty((V, 3), dtype=torch.float32, device=dev)
+            keys = torch.empty((V, 4), dtype=torch.int32, device=dev)
+            cols = torch.empty((V, 3), dtype=torch.float32, device=dev) if v.color else None
+            tris = torch.empty((T, 3), dtype=torch.int32, device=dev)
+            v.mc_emit(verts, keys, cols, tris, lo, hi)
+            ops_ = [dist.P2POp(dist.isend, t, 0, self.group) for t in (verts, keys, tris, cols) if t is not None and t.numel()]
+            if ops_:
+                for w in dist.batch_isend_irecv(ops_):
+                    w.wait()
+            profile_mark()
+            profile_mark()
             return None
-        return merge_slab_meshes(parts, [b[0] for b in self.bounds], self.ny)
+        Vt, Tt = int(nv.sum()), int(nt.sum())
+        verts = torch.empty((Vt, 3), dtype=torch.float32, device=dev)
+        keys = torch.empty((Vt, 4), dtype=torch.int32, device=dev)
+        cols = torch.empty((Vt, 3), dtype=torch.float32, device=dev) if v.color else None
+        tris = torch.empty((Tt, 3), dtype=torch.int32, device=dev)
+        vb = np.concatenate([[0], np.cumsum(nv)])
+        tb = np.concatenate([[0], np.cumsum(nt)])
+        ops_ = []
+        for r in range(1, N):
+            for t, b in ((verts, vb), (keys, vb), (tris, tb), (cols, vb)):
+                if t is not None and b[r + 1] > b[r]:
+                    ops_.append(dist.P2POp(dist.irecv, t[b[r]:b[r + 1]], r, self.group))
+        v.mc_emit(verts[:V], keys[:V], None if cols is None else cols[:V], tris[:T], lo, hi)
+        if ops_:
+            for w in dist.batch_isend_irecv(ops_):
+                w.wait()
+        profile_mark()
+        L = _lib.load()
+        ws = getattr(self, "_merge_ws", None)
+        need = L.bslam_mesh_merge_workspace_bytes(N, self.nx, self.ny)
+        if ws is None or ws.numel() < need:
+            ws = self._merge_ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        zoff = np.ascontiguousarray([b[0] for b in self.bounds], dtype=np.int32)
+        unresolved = np.zeros(1, np.int64)
+        with torch.cuda.device(dev):
+            _lib.check(L.bslam_mesh_merge(N, _lib.ptr(np.ascontiguousarray(nv)), _lib.ptr(np.ascontiguousarray(nt)), _lib.ptr(zoff), self.nx, self.ny,
+                                          _lib.ptr(keys), _lib.ptr(tris), _lib.ptr(ws), _lib.ptr(unresolved), _lib.stream_ptr(dev)))
+        if int(unresolved[0]):
+            raise RuntimeError(f"ShardedTSDF.extract_mesh: {int(unresolved[0])} unresolved cross-slab vertex references")
+        profile_mark()
+        return TriangleMesh(verts, tris, cols, keys)

@@ -386,21 +386,37 @@ class DenseTSDFVolume:
         return p
 
     # ------------------------------------------------------------------ extraction
-    def extract_triangle_mesh(self, halo_lo=None, halo_hi=None) -> TriangleMesh:
-        """Open3D `extract_triangle_mesh()` (tsdf.py:43) -- compacted marching cubes on the GPU."""
+    def mc_count(self, halo_lo=None, halo_hi=None):
+        """first phase of the marching cubes: (vertices, triangles) this box will emit (synchronises)"""
         torch = _lib.require_cuda()
         cnt = np.zeros(2, np.int64)
         with torch.cuda.device(self.device):
-            st = _lib.stream_ptr(self.device)
-            _lib.check(self._L.bslam_mc_count(self._h, _lib.ptr(halo_lo), _lib.ptr(halo_hi), _lib.ptr(cnt), st))
-            V, T = int(cnt[0]), int(cnt[1])
-            verts = torch.empty((V, 3), dtype=torch.float32, device=self.device)
-            keys = torch.empty((V, 4), dtype=torch.int32, device=self.device)
-            cols = torch.empty((V, 3), dtype=torch.float32, device=self.device) if self.color else None
-            tris = torch.empty((T, 3), dtype=torch.int32, device=self.device)
-            if V or T:
-                _lib.check(self._L.bslam_mc_emit(self._h, _lib.ptr(halo_lo), _lib.ptr(halo_hi), _lib.ptr(verts), _lib.ptr(keys),
-                                                 _lib.ptr(cols), V, _lib.ptr(tris), T, st))
+            _lib.check(self._L.bslam_mc_count(self._h, _lib.ptr(halo_lo), _lib.ptr(halo_hi), _lib.ptr(cnt), _lib.stream_ptr(self.device)))
+        return int(cnt[0]), int(cnt[1])
+
+    def mc_emit(self, verts, keys, cols, tris, halo_lo=None, halo_hi=None):
+        """second phase: write this box's mesh into caller tensors (slices of a gathered mesh, for example):
+        verts [V,3] f32, keys [V,4] i32, cols [V,3] f32 | None, tris [T,3] i32 -- all contiguous CUDA tensors"""
+        torch = _lib.require_cuda()
+        V, T = int(verts.shape[0]), int(tris.shape[0])
+        if not (V or T):
+            return
+        for t in (verts, keys, cols, tris):
+            if t is not None and not t.is_contiguous():
+                raise RuntimeError("mc_emit: output tensors must be contiguous")
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.bslam_mc_emit(self._h, _lib.ptr(halo_lo), _lib.ptr(halo_hi), _lib.ptr(verts), _lib.ptr(keys),
+                                             _lib.ptr(cols) if self.color else None, V, _lib.ptr(tris), T, _lib.stream_ptr(self.device)))
+
+    def extract_triangle_mesh(self, halo_lo=None, halo_hi=None) -> TriangleMesh:
+        """Open3D `extract_triangle_mesh()` (tsdf.py:43) -- compacted marching cubes on the GPU."""
+        torch = _lib.require_cuda()
+        V, T = self.mc_count(halo_lo, halo_hi)
+        verts = torch.empty((V, 3), dtype=torch.float32, device=self.device)
+        keys = torch.empty((V, 4), dtype=torch.int32, device=self.device)
+        cols = torch.empty((V, 3), dtype=torch.float32, device=self.device) if self.color else None
+        tris = torch.empty((T, 3), dtype=torch.int32, device=self.device)
+        self.mc_emit(verts, keys, cols, tris, halo_lo, halo_hi)
         return TriangleMesh(verts, tris, cols, keys)
 
     def extract_point_cloud(self, normals: bool = True) -> PointCloud:

@@ -90,6 +90,20 @@ BSLAM_API int bslam_colorize(const float *d_depth_m, const uint16_t *d_u16_in, i
                              double *d_vmin_vmax_out, const uint8_t *d_table_override,
                              void *d_workspace, bslam_stream_t stream);
 
+/*
+ * `colorize` for a FLOAT32 image (metres as ZoeDepth predicts them, numpy or torch -- the reference accepts
+ * both, depth_map_scaling.py:14-15): same steps as bslam_colorize, in NumPy's float32 arithmetic
+ * (percentile virtual index, lerp, normalisation all float32, as NumPy 2.x evaluates them for a float32 array);
+ * the order statistics come from an exact two-level radix select on the floats' order-preserving keys.
+ * invalid_val is compared as float (`value == invalid_val`); NaN pixels get the colormap's "bad" colour (0,0,0,0).
+ * d_workspace: bslam_colorize_f32_workspace_bytes(B).  h_vmin_vmax / d_vmin_vmax_out as in bslam_colorize.
+ */
+BSLAM_API size_t bslam_colorize_f32_workspace_bytes(int B);
+BSLAM_API int bslam_colorize_f32(const float *d_value, int B, int H, int W, uint8_t *d_rgba, const uint8_t *d_lut,
+                                 double p_lo, double p_hi, int has_invalid, float invalid_val, uint32_t bg_rgba,
+                                 const double *h_vmin_vmax, double *d_vmin_vmax_out, void *d_workspace,
+                                 bslam_stream_t stream);
+
 /* min/max-normalised 8-bit depth, `np.uint8(255*(d-min)/(max-min))`, of
  * N/3DM/slam_utils.py:250-264 (then coloured through d_lut if d_rgb != NULL: 256*3 bytes,
  * e.g. cv2.COLORMAP_JET in BGR order). d_workspace: bslam_colorize_workspace_bytes(B). */
@@ -271,6 +285,16 @@ BSLAM_API int bslam_mc_count(bslam_volume *vol, const float *d_halo_lo, const fl
 BSLAM_API int bslam_mc_emit(bslam_volume *vol, const float *d_halo_lo, const float *d_halo_hi,
                             float *d_vertices, int32_t *d_keys, float *d_colors, int64_t cap_v,
                             int32_t *d_tri, int64_t cap_t, bslam_stream_t stream);
+
+/* Gather side of the z-slab meshes ("per-slab meshes concatenated on gather", north_star): the slabs' d_keys [V][4]
+ * and d_tris [T][3] are concatenated bottom slab first (h_nv / h_nt rows each).  In place: key z becomes global
+ * (+ h_z_offsets[s]); triangle corners become global ids (+ the slab's vertex base), and the negative ids
+ * -(1 + (x*ny + y)*4 + axis) bslam_mc_emit wrote for vertices owned by the next slab's plane 0 are resolved.
+ * d_workspace: bslam_mesh_merge_workspace_bytes().  h_unresolved (optional; synchronises): number of
+ * references that found no vertex (must be 0). */
+BSLAM_API size_t bslam_mesh_merge_workspace_bytes(int n_slabs, int nx, int ny);
+BSLAM_API int bslam_mesh_merge(int n_slabs, const int64_t *h_nv, const int64_t *h_nt, const int32_t *h_z_offsets, int nx, int ny,
+                               int32_t *d_keys, int32_t *d_tris, void *d_workspace, int64_t *h_unresolved, bslam_stream_t stream);
 
 /* Replaces `TSDF.extract_pcd()` N/3DM/tsdf.py:39-40 (Open3D extract_point_cloud): interior
  * voxels with w != 0 and -0.98 <= f < 0.98, sign change towards +x/+y/+z neighbour, linear
