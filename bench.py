@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--settle", type=float, default=1.5, help="seconds of untimed steps before the warm-up (device clocks / memory settle)")
     ap.add_argument("--cpu-budget", type=float, default=6.0, help="seconds of CPU oracle work per timed CPU leg")
     ap.add_argument("--deviation", action="store_true", help="also quantify brick-restart vs literal z recurrence over all frames (slow validation kernel)")
+    ap.add_argument("--const-depth", type=int, default=0, help="EXPERIMENT: replace every frame by this constant uint16 depth (limit studies with BSLAM_EXPERIMENT; not a bench value)")
     ap.add_argument("--emulate-shard", default="", help="R/N: time rank R's shard of an N-GPU run on ONE GPU (no NCCL; development aid)")
     return ap.parse_args()
 
@@ -347,6 +348,8 @@ def main():
     if world > 1:
         dist.all_gather_into_tensor(depth_u16.view(torch.uint8), depth_u16[rank * per:(rank + 1) * per].view(torch.uint8).clone())
     depth_u16 = depth_u16[:F]
+    if args.const_depth:
+        depth_u16 = torch.full_like(depth_u16.view(torch.int16), args.const_depth).view(torch.uint16)
     log(f"rendered {F} frames")
 
     # N > 1: round-robin brick layers (rank r owns every N-th 8-voxel layer) -> balanced whatever the view
@@ -631,9 +634,21 @@ def main():
             cadence_run()
             torch.cuda.synchronize()
             dt_cad = time.perf_counter() - t0
+            # where a frame's time goes: integration stages by CUDA events, the rest is extract_pcd + Python
+            tsdf.tsdf.reset()
+            tsdf.tsdf.profile(True)
+            t1 = time.perf_counter()
+            for i in range(n_cad):
+                tsdf.build_3D_map(frames[i], intr, E[i])
+            torch.cuda.synchronize()
+            dt_int = time.perf_counter() - t1
+            st_cad, n_l = tsdf.tsdf.profile_read_stages()
+            tsdf.tsdf.profile(False)
             cadence = {"value": n_cad / dt_cad, "unit": UNIT, "frames": n_cad, "ms_per_frame": 1e3 * dt_cad / n_cad,
                        "what": "TSDF.build_3D_map(rgbd) + TSDF.extract_pcd() per frame (RGB8, unit activation), wall clock incl. Python",
-                       "points_last_frame": pts[-1], "point_counts": pts}
+                       "points_last_frame": pts[-1], "point_counts": list(pts),
+                       "integrate_only_ms_per_frame": 1e3 * dt_int / n_cad,
+                       "integrate_stage_ms_per_frame": {k: v / max(n_l, 1) for k, v in st_cad.items()}}
             log(f"SLAM cadence: {cadence['value']:.1f} frames/s ({cadence['ms_per_frame']:.2f} ms per integrate + extract_pcd)")
             del tsdf, frames
 
@@ -735,6 +750,21 @@ def main():
                                        "mesh_vertices": int(gm.vertices.shape[0]), "mesh_triangles": int(gm.triangles.shape[0]), "occupied_voxels": int(Sv.occupied()),
                                        "oracle": "oracle/o3d_oracle.c orc_scalable_integrate (z_restart 0 = Open3D's literal per-unit recurrence) + orc_extract_mesh"}
             del Sv, g, t, w, c, gm, om
+        if cadence is not None:
+            # the same cadence on the CPU oracle (ScalableTSDFVolume rule + extract_point_cloud), first frames of the trajectory
+            n_c = 3
+            d3, c3 = depth_u16[:n_c].cpu().numpy(), S.render(cfg["surface"], E[:n_c], K=cfg["K"], W=W, H=H, device=dev, with_color=True)[1].cpu().numpy()
+            Cv = oracle.o3d.Volume(res, vl, trunc, unit_origin(cfg["origin"], vl), with_color=True)
+            cp, t0 = [], time.perf_counter()
+            for i in range(n_c):
+                Cv.integrate_scalable(oracle.o3d.depth_from_u16(d3[i]), cfg["K"], E[i], rgb=c3[i])
+                cp.append(int(len(Cv.extract_points()["points"])))
+            dt_c = time.perf_counter() - t0
+            cadence["cpu_oracle"] = {"value": n_c / dt_c, "unit": UNIT, "frames": n_c, "point_counts": cp,
+                                     "point_counts_equal_gpu": cp == cadence["point_counts"][:n_c], "cores": legs["cores"]}
+            cadence["point_counts"] = cadence["point_counts"][:8] + ["..."] + cadence["point_counts"][-2:]
+            parity["slam_cadence_point_counts_equal"] = cadence["cpu_oracle"]["point_counts_equal_gpu"]
+            del Cv
         log(f"parity: {json.dumps(parity)}")
         cpu = {"value": legs["dense_fps"], "unit": UNIT, "cores": legs["cores"], "kind": "port",
                "sample": f"{legs['dense_frames']} frames drawn evenly (seeded shuffle, {args.cpu_budget:g} s budget) from the {F}-frame trajectory, {res}^3 dense sweep per "

@@ -1,5 +1,18 @@
 """PLY writers for the 3DM outputs (`o3d.io.write_point_cloud` / `write_triangle_mesh` of
-N/3DM/tsdf.py:37,52).  Binary little-endian PLY, the format Open3D writes for `.ply` paths."""
+N/3DM/tsdf.py:37,52).
+
+Byte layout restated from Open3D's PLY writers (FilePLY.cpp: WritePointCloudToPLY / WriteTriangleMeshToPLY
+through rply, default `write_ascii=False`), so that a file written here equals the one the reference would
+have written for the same geometry:
+  header   "ply" / "format binary_little_endian 1.0" / "comment Created by Open3D" / "element vertex N" /
+           "property double x|y|z" [/ "property double nx|ny|nz" when normals exist]
+           [/ "property uchar red|green|blue" when colours exist]
+           [/ "element face M" / "property list uchar uint vertex_indices"] / "end_header", '\n' line ends;
+  vertices packed little-endian records in that property order; colours = utility::ColorToUint8 =
+           round(clamp(c, 0, 1) * 255);
+  faces    uchar 3 + three uint32 indices.
+Open3D is not installable here, so the layout is pinned by tests/test_capi_and_host.py against this
+restatement (header bytes and record offsets), not against a file Open3D wrote."""
 from __future__ import annotations
 
 import numpy as np
@@ -8,7 +21,7 @@ from .geometry import to_numpy
 
 
 def _ply_header(n_vert, props, n_face=None):
-    lines = ["ply", "format binary_little_endian 1.0", "comment Created by bodyslam_b200", f"element vertex {n_vert}"]
+    lines = ["ply", "format binary_little_endian 1.0", "comment Created by Open3D", f"element vertex {n_vert}"]
     lines += [f"property {t} {n}" for t, n in props]
     if n_face is not None:
         lines += [f"element face {n_face}", "property list uchar uint vertex_indices"]
@@ -30,7 +43,7 @@ def _vertex_block(xyz, normals=None, colors=None):
     if normals is not None:
         rec["nx"], rec["ny"], rec["nz"] = normals[:, 0], normals[:, 1], normals[:, 2]
     if colors is not None:
-        c8 = np.clip(np.asarray(colors, dtype=np.float64) * 255.0, 0, 255).astype(np.uint8)
+        c8 = np.floor(np.clip(np.asarray(colors, dtype=np.float64), 0.0, 1.0) * 255.0 + 0.5).astype(np.uint8)   # utility::ColorToUint8 (std::round)
         rec["red"], rec["green"], rec["blue"] = c8[:, 0], c8[:, 1], c8[:, 2]
     return rec, props
 

@@ -85,10 +85,43 @@ def test_ply_writers_round_trip(tmp_path):
     write_triangle_mesh(str(tmp_path / "m.ply"), TriangleMesh(v, t, c))
     verts, faces = read_ply(str(tmp_path / "m.ply"))
     assert np.allclose(np.stack([verts["x"], verts["y"], verts["z"]], 1), v) and np.array_equal(faces, t)
-    assert np.array_equal(verts["red"], (c[:, 0].astype(np.float64) * 255).astype(np.uint8))
+    assert np.array_equal(verts["red"], np.floor(c[:, 0].astype(np.float64) * 255 + 0.5).astype(np.uint8))
     write_point_cloud(str(tmp_path / "p.ply"), PointCloud(v, None, v))
     verts, faces = read_ply(str(tmp_path / "p.ply"))
     assert faces is None and np.allclose(verts["nz"], v[:, 2])
+
+
+def test_ply_bytes_follow_open3d_writer_layout(tmp_path):
+    """o3d.io.write_triangle_mesh / write_point_cloud (N/3DM/tsdf.py:37,52) for a `.ply` path: rply binary
+    little-endian, comment "Created by Open3D", double coordinates (+ double normals), uchar colours =
+    round(clamp(c) * 255), faces as uchar count + uint32 indices -- checked byte by byte against a hand-packed file"""
+    import struct
+    from bodyslam_b200.geometry import PointCloud, TriangleMesh
+    from bodyslam_b200.io import write_point_cloud, write_triangle_mesh
+    v = np.array([[0.0, 1.5, -2.25], [1e-3, 2.0, 3.0], [4.0, 5.0, 6.0]], np.float32)
+    c = np.array([[0.0, 0.5, 1.0], [0.2, 0.999, 1.7], [-0.1, 0.25, 0.75]], np.float32)
+    t = np.array([[0, 1, 2], [2, 1, 0]], np.int32)
+    write_triangle_mesh(str(tmp_path / "m.ply"), TriangleMesh(v, t, c))
+    head = (b"ply\nformat binary_little_endian 1.0\ncomment Created by Open3D\nelement vertex 3\nproperty double x\nproperty double y\n"
+            b"property double z\nproperty uchar red\nproperty uchar green\nproperty uchar blue\nelement face 2\n"
+            b"property list uchar uint vertex_indices\nend_header\n")
+    body = b""
+    for p, col in zip(v, c):
+        body += struct.pack("<3d", *[float(x) for x in p])
+        body += struct.pack("<3B", *[int(np.floor(min(1.0, max(0.0, float(x))) * 255.0 + 0.5)) for x in col])
+    for tri in t:
+        body += struct.pack("<B3I", 3, *[int(i) for i in tri])
+    assert open(tmp_path / "m.ply", "rb").read() == head + body
+    n = np.array([[0, 0, 1], [0, 1, 0], [1, 0, 0]], np.float32)
+    write_point_cloud(str(tmp_path / "p.ply"), PointCloud(v, c, n))
+    head = (b"ply\nformat binary_little_endian 1.0\ncomment Created by Open3D\nelement vertex 3\nproperty double x\nproperty double y\n"
+            b"property double z\nproperty double nx\nproperty double ny\nproperty double nz\nproperty uchar red\nproperty uchar green\n"
+            b"property uchar blue\nend_header\n")
+    body = b""
+    for p, nn, col in zip(v, n, c):
+        body += struct.pack("<6d", *[float(x) for x in p], *[float(x) for x in nn])
+        body += struct.pack("<3B", *[int(np.floor(min(1.0, max(0.0, float(x))) * 255.0 + 0.5)) for x in col])
+    assert open(tmp_path / "p.ply", "rb").read() == head + body
 
 
 def test_depth_estimator_interface_keeps_reference_surface(tmp_path):

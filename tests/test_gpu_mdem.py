@@ -160,3 +160,59 @@ def test_backproject_matches_oracle(cuda, stride):
     want = pixel_to_3d(u, v, float(depth[0][v, u]), *sc["K"])
     if depth[0][v, u] > 0:
         assert np.abs(p[v * sc["W"] + u].cpu().numpy() - want).max() < 1e-5
+
+
+@pytest.mark.parametrize("case", ["metres", "wide", "tiny", "constant", "negative", "two_values", "ties"])
+def test_colorize_float32_metres_matches_numpy(cuda, case):
+    """`colorize` on a FLOAT32 image (ZoeDepth's metres tensor, depth_map_scaling.py:14-15), numpy and torch, CPU and
+    CUDA: NumPy's float32 percentile / normalisation and matplotlib's index rule, reproduced exactly (RGBA bytes
+    and vmin / vmax bit for bit) by the two-level radix select."""
+    rng = np.random.default_rng(sum(map(ord, case)))
+    if case == "metres":
+        yy, xx = np.mgrid[0:480, 0:640]
+        d = (0.4 + 1.9 * (0.5 + 0.5 * np.sin(xx / 37.0) * np.cos(yy / 53.0)) + rng.normal(0, 1e-3, (480, 640))).astype(np.float32)
+        d[rng.uniform(size=d.shape) < 0.05] = 0
+    elif case == "wide":
+        d = np.exp(rng.uniform(-20, 20, (123, 457))).astype(np.float32)
+        d[::9, ::4] = 0
+    elif case == "tiny":
+        d = rng.uniform(0.1, 3.0, (3, 5)).astype(np.float32)
+        d[1, 1] = 0
+    elif case == "constant":
+        d = np.full((64, 64), 1.2345, np.float32)
+        d[::7, ::5] = 0
+    elif case == "negative":
+        d = rng.normal(0.0, 5.0, (200, 300)).astype(np.float32)
+        d[d == 0] = 1e-3
+        d[::11, ::3] = 0
+    elif case == "two_values":
+        d = np.where(rng.uniform(size=(100, 100)) < 0.5, 1.0, 2.5).astype(np.float32)
+    else:   # many exact ties around the percentile ranks
+        d = np.round(rng.uniform(0.5, 2.0, (240, 320)), 2).astype(np.float32)
+        d[::5, ::5] = 0
+    lut = mdem.get_cmap_lut("viridis")
+    ref, idx, vmin, vmax = oracle.mdem.colorize(d.copy(), lut, invalid_val=0, return_index=True)
+    out = mdem.colorize(d.copy(), cmap="viridis", invalid_val=0)
+    assert out.dtype == np.uint8 and out.shape == ref.shape
+    _, stats = ops.colorize_f32(lut, d, invalid_val=0, return_stats=True)
+    assert stats.cpu().numpy().tolist() == [[float(vmin), float(vmax)]], (stats.cpu().numpy().tolist(), vmin, vmax)
+    assert np.array_equal(out, ref)
+    # torch CPU / CUDA tensors with singleton dims, like a network output [1,1,H,W]
+    for t in (torch.from_numpy(d)[None, None], torch.from_numpy(d).to(cuda)[None]):
+        assert np.array_equal(mdem.colorize(t, cmap="viridis", invalid_val=0), ref)
+    # explicit vmin / vmax, gamma, an explicit invalid mask
+    ref2 = oracle.mdem.colorize(d.copy(), lut, vmin=0.5, vmax=2.0, invalid_val=0, gamma_corrected=True)
+    assert np.array_equal(mdem.colorize(d.copy(), vmin=0.5, vmax=2.0, cmap="viridis", invalid_val=0, gamma_corrected=True), ref2)
+    m = rng.uniform(size=d.shape) < 0.2
+    ref3 = oracle.mdem.colorize(d.copy(), lut, invalid_mask=m)
+    assert np.array_equal(mdem.colorize(d.copy(), cmap="viridis", invalid_mask=m), ref3)
+
+
+def test_colorize_float32_batch_is_per_image(cuda):
+    rng = np.random.default_rng(3)
+    d = rng.uniform(0.2, 4.0, (5, 96, 128)).astype(np.float32) * np.arange(1, 6, dtype=np.float32)[:, None, None]
+    d[:, ::6, ::7] = 0
+    lut = mdem.get_cmap_lut("jet")
+    out = ops.colorize_f32(lut, d, invalid_val=0).cpu().numpy()
+    for b in range(5):
+        assert np.array_equal(out[b], oracle.mdem.colorize(d[b].copy(), lut, invalid_val=0))
