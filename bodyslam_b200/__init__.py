@@ -18,7 +18,7 @@ def __getattr__(name):  # lazy: keep `import bodyslam_b200` light and torch-free
     import importlib
 
     table = {
-        "TSDF": "tsdf", "DenseTSDFVolume": "tsdf",
+        "TSDF": "tsdf", "MAP": "tsdf", "DenseTSDFVolume": "tsdf",
         "RGBD": "slam_utils", "update_map_after_pg": "slam_utils", "get_o3d_intrinsic": "slam_utils",
         "compute_curr_estimate_global_pose": "slam_utils", "pixel_to_3d": "slam_utils",
         "colorize": "mdem", "process_image": "mdem", "process_images": "mdem", "DepthEstimator": "mdem",

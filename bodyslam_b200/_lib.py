@@ -58,6 +58,10 @@ _SIGNATURES = {
     "bslam_mc_emit": (C.c_int, [_p, _p, _p, _p, _p, _p, C.c_int64, _p, C.c_int64, _p]),
     "bslam_mesh_merge_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "bslam_mesh_merge": (C.c_int, [C.c_int, _p, _p, _p, C.c_int, C.c_int, _p, _p, _p, _p, _p]),
+    "bslam_vbg_workspace_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "bslam_vbg_integrate": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_int, _p, _p, _p, C.c_float, C.c_float, _p, _p, _p]),
+    "bslam_vbg_stats": (C.c_int, [_p, _p, _p]),
+    "bslam_tsdf_set_extract_flavour": (C.c_int, [_p, C.c_float, C.c_double]),
     "bslam_points_count": (C.c_int, [_p, _p, _p]),
     "bslam_points_emit": (C.c_int, [_p, _p, _p, _p, _p, C.c_int64, _p]),
 }

@@ -79,6 +79,11 @@ struct VolView {
     int u0[3];
     int nux, nuy, nuz;   // units per axis (z: of the whole grid when the box is a z-shard)
     double unit_len;
+    // surface-extraction flavour: a voxel is valid when weight > w_min (0: Open3D's legacy `weight != 0`; the tensor
+    // pipeline of `MAP` uses weight >= 3); vertices / points sit at (index + pos_half) * voxel_length (legacy 0.5 = voxel
+    // centres, tensor pipeline 0 = voxel corners)
+    float w_min;
+    double pos_half;
 };
 
 // world position (f32, as Open3D narrows it) of the centre of GLOBAL voxel index g along `axis`:

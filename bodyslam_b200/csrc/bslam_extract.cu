@@ -87,7 +87,7 @@ __device__ __forceinline__ BrickClass classify_brick(const VolView &v, const flo
         const int ry = i % kR, rx = (i / kR) % kR, rz = i / (kR * kR);
         const float2 t = fetch_voxel(v, halo_lo, halo_hi, bx * 8 - 1 + rx, by * 8 - 1 + ry, bz * 8 - 1 + rz);
         s_t[i] = t.x;
-        s_ok[i] = t.y != 0.0f;
+        s_ok[i] = t.y > v.w_min;
     }
     __syncthreads();
     // cube validity for the 9^3 cubes based at region coords [0,9)^3
@@ -202,7 +202,7 @@ __global__ void __launch_bounds__(kBrickVox) mc_brick_kernel(const VolView v, do
         const double f0 = fabs((double)s_t[ridx(rx, ry, rz)]);
         const double f1 = fabs((double)s_t[ridx(rx + (a == 0), ry + (a == 1), rz + (a == 2))]);
         // Open3D: pt = half + vl * (x,y,z) (f64); pt[axis] += f0 * vl / (f0 + f1); + origin
-        double pt[3] = {0.5 * vld + vld * X, 0.5 * vld + vld * Y, 0.5 * vld + vld * (Z + v.gz0)};
+        double pt[3] = {v.pos_half * vld + vld * X, v.pos_half * vld + vld * Y, v.pos_half * vld + vld * (Z + v.gz0)};
         pt[a] += f0 * vld / (f0 + f1);
         vertices[3 * id + 0] = (float)(pt[0] + v.ox);
         vertices[3 * id + 1] = (float)(pt[1] + v.oy);
@@ -399,12 +399,12 @@ __global__ void mc_list_kernel(int64_t nb, McScratch sc) {
 }
 
 // ---------------------------------------------------------------- surface points (A.5)
-__device__ __forceinline__ bool pt_ok(float2 t) { return t.y != 0.0f && t.x < 0.98f && t.x >= -0.98f; }
+__device__ __forceinline__ bool pt_ok(const VolView &v, float2 t) { return t.y > v.w_min && t.x < 0.98f && t.x >= -0.98f; }
 
 __device__ double tsdf_at(const VolView &v, double vl, const double *p) {
     int idx[3]; double r[3];
     for (int i = 0; i < 3; ++i) {
-        const double g = p[i] / vl - 0.5;
+        const double g = p[i] / vl - v.pos_half;
         idx[i] = (int)floor(g);
         r[i] = g - (double)idx[i];
     }
@@ -436,13 +436,13 @@ __global__ void __launch_bounds__(kBrickVox) points_brick_kernel(const VolView v
     float2 t0 = make_float2(0.f, 0.f), t1[3];
     if (X >= 1 && Y >= 1 && Z >= 1 && X < v.nx - 1 && Y < v.ny - 1 && Z < v.nz - 1) {
         t0 = v.vox[b * kBrickVox + tid];
-        if (pt_ok(t0)) {
+        if (pt_ok(v, t0)) {
 #pragma unroll
             for (int a = 0; a < 3; ++a) {
                 const int c1[3] = {X + (a == 0), Y + (a == 1), Z + (a == 2)};
                 if (!(c1[a] < n[a] - 1)) continue;
                 t1[a] = v.vox[voxel_slot(v, c1[0], c1[1], c1[2])];
-                if (pt_ok(t1[a]) && t0.x * t1[a].x < 0) bits |= 1u << a;
+                if (pt_ok(v, t1[a]) && t0.x * t1[a].x < 0) bits |= 1u << a;
             }
         }
     }
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(kBrickVox) points_brick_kernel(const VolView v
     __syncthreads();
     if (!EMIT || !cnt) continue;
     int64_t o = (int64_t)sc.vbase[b] + s_w[wid] + (inc - cnt);
-    const double half = vl * 0.5, half_gap = 0.99 * vl;
+    const double half = vl * v.pos_half, half_gap = 0.99 * vl;
     const double p0[3] = {half + vl * X, half + vl * Y, half + vl * Z};
 #pragma unroll
     for (int a = 0; a < 3; ++a) {

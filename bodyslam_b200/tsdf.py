@@ -508,3 +508,101 @@ class TSDF:
 
         mesh = self.extract_mesh()
         write_triangle_mesh(saving_path, mesh)
+
+
+class MAP:
+    """Drop-in for the reference's `MAP` (N/3DM/tsdf.py:56-108): the tensor-pipeline reconstruction
+    (`o3d.t.pipelines.slam.Model`: VoxelBlockGrid of 16^3 blocks, projective TSDF, `depth_max` cut,
+    `trunc_voxel_multiplier`).  Same constructor and methods; the blocks live in a bounded dense box
+    (extra kwargs `resolution`, `origin`, `color`) instead of Open3D's hash map of `block_count` blocks
+    (`block_count` is accepted and ignored; ray points that leave the box are counted, see `clip_stats`).
+    `synthesize_model_frame` (ray casting into `raycast_frame`, whose result the reference discards) is not
+    provided.  Extraction follows the tensor pipeline's defaults: weight threshold 3, vertices on voxel corners.
+    """
+
+    BLOCK = 16
+
+    def __init__(self, width, height, intrinsic, device, depth_scale, voxel_size=0.0058, block_count=40000, trunc_voxel_multiplier=8.0,
+                 resolution=512, origin=None, color: bool = True, weight_threshold: float = 3.0):
+        torch = _lib.require_cuda()
+        self.width, self.height = int(width), int(height)
+        K = np.asarray(to_numpy(intrinsic), dtype=np.float64) if not hasattr(intrinsic, "intrinsic_matrix") else np.asarray(intrinsic.intrinsic_matrix, dtype=np.float64)
+        if K.shape != (3, 3):
+            raise RuntimeError("[MAP] intrinsic must be a 3x3 matrix (the tensor pipeline takes o3d.core.Tensor(K))")
+        self._K = np.array([K[0, 0], K[1, 1], K[0, 2], K[1, 2]], dtype=np.float64)
+        self.depth_scale = float(depth_scale)
+        self.voxel_size = float(voxel_size)
+        self.block_count = int(block_count)
+        self.trunc_voxel_multiplier = float(trunc_voxel_multiplier)
+        dev = str(device).lower() if device is not None else None
+        dev = ops._device(dev if (dev is not None and "cuda" in dev) else None)
+        res = (int(resolution),) * 3 if np.isscalar(resolution) else tuple(int(r) for r in resolution)
+        if any(r % self.BLOCK for r in res):
+            raise RuntimeError(f"[MAP] the box must consist of whole {self.BLOCK}^3 blocks")
+        if origin is None:
+            bs = self.voxel_size * self.BLOCK
+            origin = tuple(-(r // (2 * self.BLOCK)) * bs for r in res)
+        # sdf_trunc of the underlying box is only used by the legacy integrator; keep it consistent anyway
+        self.model = DenseTSDFVolume(self.voxel_size, self.voxel_size * self.trunc_voxel_multiplier, res, origin, color=color, device=dev)
+        _lib.check(self.model._L.bslam_tsdf_set_extract_flavour(self.model._h, float(weight_threshold), 0.0))
+        self._ws = torch.zeros(self.model._L.bslam_vbg_workspace_bytes(*res), dtype=torch.uint8, device=dev)
+        self.poses = {}
+
+    def integrate_batch(self, depth_u16, color, poses, depth_max, update_counts=None):
+        """F frames in order: depth_u16 [F,H,W] uint16 (raw, divided by depth_scale in the kernel), color
+        [F,H,W,3] uint8 | None, poses [F,4,4] camera->world, depth_max scalar or [F]."""
+        torch = _lib.require_cuda()
+        vol = self.model
+        if ops._dtype_name(depth_u16) != "uint16":
+            raise RuntimeError("[MAP::Integrate] Unsupported image format.")
+        d = ops.as_cuda(depth_u16, torch.uint16, vol.device)
+        if d.dim() == 2:
+            d = d.unsqueeze(0)
+        F = d.shape[0]
+        if d.shape[1] != self.height or d.shape[2] != self.width:
+            raise RuntimeError("[MAP::Integrate] Unsupported image format.")
+        c = None
+        if vol.color:
+            if color is None or ops._dtype_name(color) != "uint8":
+                raise RuntimeError("[MAP::Integrate] Unsupported image format.")
+            c = ops.as_cuda(color, torch.uint8, vol.device)
+            if c.numel() != F * self.height * self.width * 3:
+                raise RuntimeError("[MAP::Integrate] Unsupported image format.")
+        P = np.ascontiguousarray(np.asarray(to_numpy(poses), dtype=np.float64).reshape(-1, 16))
+        if P.shape[0] != F:
+            raise RuntimeError(f"MAP.integrate_batch: {F} frames but {P.shape[0]} poses")
+        dm = np.ascontiguousarray(np.broadcast_to(np.asarray(depth_max, dtype=np.float64), (F,)))
+        with torch.cuda.device(vol.device):
+            _lib.check(vol._L.bslam_vbg_integrate(vol._h, _lib.ptr(d), _lib.ptr(c), F, self.height, self.width, _lib.ptr(self._K), _lib.ptr(P),
+                                                  _lib.ptr(dm), self.depth_scale, self.trunc_voxel_multiplier, _lib.ptr(self._ws),
+                                                  _lib.ptr(update_counts), _lib.stream_ptr(vol.device)))
+        vol.frames_integrated += F
+
+    def integrate(self, curr_rgbd, i, curr_global_pose):
+        """reference signature (tsdf.py:71): `curr_rgbd` is an `RGBD` (uses `.o3d_t_depth`, `.o3d_t_color`,
+        `.depth_max`), `curr_global_pose` the 4x4 camera->world pose of frame i (`update_frame_pose`)."""
+        pose = np.asarray(to_numpy(curr_global_pose), dtype=np.float64).reshape(4, 4)
+        self.poses[int(i)] = pose
+        self.integrate_batch(curr_rgbd.o3d_t_depth, curr_rgbd.o3d_t_color if self.model.color else None, pose[None], curr_rgbd.depth_max)
+
+    def clip_stats(self):
+        """ray points of the block activation seen / outside the bounded box (the reference's hash map is unbounded)"""
+        out = (C.c_ulonglong * 2)()
+        _lib.check(self.model._L.bslam_vbg_stats(_lib.ptr(self._ws), out, _lib.stream_ptr(self.model.device)))
+        return {"points": int(out[0]), "outside": int(out[1])}
+
+    def extract_pcd(self):
+        return self.model.extract_point_cloud()
+
+    def extract_mesh(self) -> TriangleMesh:
+        return self.model.extract_triangle_mesh()
+
+    def save_pcd(self, saving_path: str):
+        from .io import write_point_cloud
+
+        write_point_cloud(saving_path, self.extract_pcd())
+
+    def save_mesh(self, saving_path: str):
+        from .io import write_triangle_mesh
+
+        write_triangle_mesh(saving_path, self.extract_mesh())

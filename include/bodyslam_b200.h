@@ -296,6 +296,30 @@ BSLAM_API size_t bslam_mesh_merge_workspace_bytes(int n_slabs, int nx, int ny);
 BSLAM_API int bslam_mesh_merge(int n_slabs, const int64_t *h_nv, const int64_t *h_nt, const int32_t *h_z_offsets, int nx, int ny,
                                int32_t *d_keys, int32_t *d_tris, void *d_workspace, int64_t *h_unresolved, bslam_stream_t stream);
 
+/* ------------------------------------------------------------------ tensor-pipeline integrator (row f4)
+ * Replaces `MAP.integrate(curr_rgbd, i, curr_global_pose)` N/3DM/tsdf.py:71-83, i.e. Open3D
+ * `t.pipelines.slam.Model.integrate(frame, depth_scale, depth_max, trunc_voxel_multiplier)` on a VoxelBlockGrid of
+ * 16^3 blocks (`MAP.__init__` N/3DM/tsdf.py:57-69), for F frames in order, on the bounded dense box `vol`
+ * (origin on the world block grid: origin = k * 16 * voxel_size; created without unit activation):
+ * blocks are activated per frame by the depth-touch rule (every 4th pixel, 4 points along the ray over
+ * [d - trunc, d + trunc], trunc = trunc_voxel_multiplier * voxel_size), activated voxels get the PROJECTIVE update
+ * sdf = depth - z with the depth_max cut (see csrc/bslam_vbg.cu).  d_depth_u16 [F][H][W] raw depth (divided by
+ * depth_scale in the kernel, like Open3D), d_rgb optional [F][H][W][3] u8 (colour volumes), h_poses [F][16] f64
+ * camera->world (T_frame_to_model), h_depth_max [F] f64 (`curr_rgbd.depth_max`).  d_workspace:
+ * bslam_vbg_workspace_bytes() bytes, ZEROED by the caller once; its first 16 bytes accumulate {ray points
+ * seen, ray points outside the box} (bslam_vbg_stats; the reference's hash map is unbounded).
+ * `synthesize_model_frame` (ray casting, whose result MAP discards) is not provided. */
+BSLAM_API size_t bslam_vbg_workspace_bytes(int nx, int ny, int nz);
+BSLAM_API int bslam_vbg_integrate(bslam_volume *vol, const uint16_t *d_depth_u16, const uint8_t *d_rgb, int F, int H, int W,
+                                  const double *h_K, const double *h_poses, const double *h_depth_max, float depth_scale,
+                                  float trunc_voxel_multiplier, void *d_workspace, unsigned long long *d_update_counts,
+                                  bslam_stream_t stream);
+BSLAM_API int bslam_vbg_stats(const void *d_workspace, unsigned long long *h_stat2, bslam_stream_t stream);
+/* Surface-extraction flavour of bslam_mc_* / bslam_points_*: a voxel is valid when weight >= weight_threshold
+ * (0 = Open3D's legacy `weight != 0`; the tensor pipeline's extract_triangle_mesh / extract_point_cloud default is 3)
+ * and vertices sit at (index + vertex_offset) * voxel_length (legacy 0.5 = voxel centres; tensor pipeline 0). */
+BSLAM_API int bslam_tsdf_set_extract_flavour(bslam_volume *vol, float weight_threshold, double vertex_offset);
+
 /* Replaces `TSDF.extract_pcd()` N/3DM/tsdf.py:39-40 (Open3D extract_point_cloud): interior
  * voxels with w != 0 and -0.98 <= f < 0.98, sign change towards +x/+y/+z neighbour, linear
  * zero crossing; normals from the 0.99-voxel central difference of the trilinear TSDF.

@@ -43,6 +43,10 @@ def lib():
         L.orc_extract_points.restype = C.c_int64
         L.orc_extract_points.argtypes = [p, p, p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, p,
                                          p, p, p, p, C.c_int64]
+        L.orc_set_extract_flavour.argtypes = [C.c_double, C.c_double]
+        L.orc_vbg_integrate.restype = C.c_int64
+        L.orc_vbg_integrate.argtypes = [p, p, p, C.c_int, C.c_int, C.c_int, p, C.c_double, C.c_double, p, p, C.c_int, C.c_int, p, p,
+                                        C.c_double, C.c_double, p]
         L.orc_count_occupied.restype = C.c_int64
         L.orc_count_occupied.argtypes = [p, C.c_size_t]
         _lib = L
@@ -65,6 +69,12 @@ def set_scalable_schedule(open3d_like: bool) -> None:
     """threading of `Volume.integrate_scalable`: True = Open3D's own (touched units one after the other, OpenMP
     only over the x loop inside a unit), False (default) = units spread over the threads (faster; same result)"""
     lib().orc_set_scalable_schedule(0 if open3d_like else 1)
+
+
+def set_extract_flavour(weight_threshold: float = 0.0, pos_half: float = 0.5) -> None:
+    """flavour of extract_mesh / extract_points: legacy Open3D (weight != 0, voxel centres) by default; the tensor
+    pipeline behind `MAP` uses weight >= 3 and voxel corners (3.0, 0.0).  Global: reset it after use."""
+    lib().orc_set_extract_flavour(float(weight_threshold), float(pos_half))
 
 
 def depth_from_u16(depth_u16, depth_scale=1000.0, depth_trunc=3.0):
@@ -144,6 +154,27 @@ class Volume:
                                          self.nx, self.ny, self.nz, _ptr(u0), int(unit_res), int(stride), self.voxel_length,
                                          self.sdf_trunc, _ptr(d), _ptr(c), W, H, _ptr(Kd), _ptr(E), _ptr(M), int(z_restart), _ptr(touched))
         return (n, touched.reshape(self.nx // unit_res, self.ny // unit_res, self.nz // unit_res)) if return_touched else n
+
+    def integrate_vbg(self, depth_u16, K, pose, rgb=None, depth_scale=1000.0, depth_max=3.0, trunc_voxel_multiplier=8.0, return_touched=False):
+        """`MAP.integrate` (N/3DM/tsdf.py:71-83): Open3D tensor VoxelBlockGrid semantics (16^3 blocks, depth-touch
+        activation, projective sdf, depth_max) on this dense box; `pose` = camera->world 4x4 (T_frame_to_model);
+        voxel_length is the voxel_size, the box origin must sit on the world block grid.  `sdf_trunc` is unused."""
+        d = np.ascontiguousarray(depth_u16, dtype=np.uint16)
+        H, W = d.shape
+        Kd = np.ascontiguousarray(K, dtype=np.float64)
+        P = np.ascontiguousarray(pose, dtype=np.float64)
+        c = None if rgb is None else np.ascontiguousarray(rgb, dtype=np.uint8)
+        bs = self.voxel_length * 16
+        b0 = np.rint(self.origin / bs)
+        if self.gz0 or np.abs(b0 * bs - self.origin).max() > 1e-9 * max(1.0, np.abs(self.origin).max()):
+            raise ValueError("the box origin must sit on the world block grid (multiples of 16 voxels)")
+        b0 = np.ascontiguousarray(b0, dtype=np.int32)
+        nb = [(n + 15) // 16 for n in (self.nx, self.ny, self.nz)]
+        touched = np.zeros(nb[0] * nb[1] * nb[2], np.uint8)
+        n = lib().orc_vbg_integrate(_ptr(self.tsdf), _ptr(self.weight), _ptr(self.color if c is not None else None), self.nx, self.ny, self.nz,
+                                    _ptr(b0), self.voxel_length, float(trunc_voxel_multiplier), _ptr(d), _ptr(c), W, H, _ptr(Kd), _ptr(P),
+                                    float(depth_scale), float(depth_max), _ptr(touched))
+        return (n, touched.reshape(nb)) if return_touched else n
 
     def grid(self, name="tsdf"):
         return getattr(self, name).reshape(self.nx, self.ny, self.nz)

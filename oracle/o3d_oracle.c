@@ -320,6 +320,14 @@ ORC_API int64_t orc_scalable_integrate(float *tsdf, float *weight, float *color,
     return updated;
 }
 
+/* Surface-extraction flavour (row f4): a voxel is valid when weight >= g_w_thr (0: the legacy rule weight != 0),
+ * vertices / points sit at (index + g_pos_half) * voxel_length.  Legacy Open3D: 0 / 0.5; the tensor pipeline behind
+ * `MAP` (N/3DM/tsdf.py:85-89: voxel_grid.extract_triangle_mesh() / extract_point_cloud(), weight_threshold = 3): 3 / 0. */
+static float g_w_thr = 0.0f;
+static double g_pos_half = 0.5;
+ORC_API void orc_set_extract_flavour(double weight_threshold, double pos_half) { g_w_thr = (float)weight_threshold; g_pos_half = pos_half; }
+static int orc_valid_w(float w) { return g_w_thr > 0.0f ? (w >= g_w_thr) : (w != 0.0f); }
+
 /* ------------------------------------------------------------------ A.4 */
 typedef struct {
     uint64_t *keys;
@@ -363,7 +371,7 @@ ORC_API void orc_extract_mesh(const float *tsdf, const float *weight, const floa
                               int ny, int nz, int gz0, double voxel_length, const double *origin,
                               double *out_v, int32_t *out_key, double *out_c, int64_t cap_v,
                               int32_t *out_t, int32_t *out_tz, int64_t cap_t, int64_t *counts) {
-    const double half = voxel_length * 0.5;
+    const double half = voxel_length * g_pos_half;
     orc_map map; map_init(&map, 1u << 16);
     int64_t nv = 0, nt = 0;
     for (int x = 0; x < nx - 1; ++x)
@@ -373,7 +381,7 @@ ORC_API void orc_extract_mesh(const float *tsdf, const float *weight, const floa
                 float f[8]; size_t id[8];
                 for (int i = 0; i < 8; ++i) {
                     id[i] = ((size_t)(x + orc_shift[i][0]) * ny + (y + orc_shift[i][1])) * nz + (z + orc_shift[i][2]);
-                    if (weight[id[i]] == 0.0f) { ok = 0; break; }
+                    if (!orc_valid_w(weight[id[i]])) { ok = 0; break; }
                     f[i] = tsdf[id[i]];
                     if (f[i] < 0.0f) cube_index |= (1 << i);
                 }
@@ -426,7 +434,7 @@ ORC_API void orc_extract_mesh(const float *tsdf, const float *weight, const floa
 static double tsdf_at(const float *tsdf, int ny, int nz, double voxel_length, const double *p) {
     int idx[3]; double r[3];
     for (int i = 0; i < 3; ++i) {
-        const double g = p[i] / voxel_length - 0.5;
+        const double g = p[i] / voxel_length - g_pos_half;
         idx[i] = (int)floor(g);
         r[i] = g - (double)idx[i];
     }
@@ -455,7 +463,7 @@ ORC_API int64_t orc_extract_points(const float *tsdf, const float *weight, const
                                    int nx, int ny, int nz, int gz0, double voxel_length,
                                    const double *origin, double *out_p, double *out_n,
                                    double *out_c, int32_t *out_key, int64_t cap) {
-    const double half = voxel_length * 0.5;
+    const double half = voxel_length * g_pos_half;
     const double half_gap = 0.99 * voxel_length;
     const int n[3] = {nx, ny, nz};
     int64_t np = 0;
@@ -465,7 +473,7 @@ ORC_API int64_t orc_extract_points(const float *tsdf, const float *weight, const
                 const int idx0[3] = {x, y, z};
                 const size_t i0 = ((size_t)x * ny + y) * nz + z;
                 const float w0 = weight[i0], f0 = tsdf[i0];
-                if (!(w0 != 0.0f && f0 < 0.98f && f0 >= -0.98f)) continue;
+                if (!(orc_valid_w(w0) && f0 < 0.98f && f0 >= -0.98f)) continue;
                 const double p0[3] = {half + voxel_length * x, half + voxel_length * y, half + voxel_length * z};
                 for (int i = 0; i < 3; ++i) {
                     int idx1[3] = {x, y, z};
@@ -473,7 +481,7 @@ ORC_API int64_t orc_extract_points(const float *tsdf, const float *weight, const
                     if (!(idx1[i] < n[i] - 1)) continue;
                     const size_t i1 = ((size_t)idx1[0] * ny + idx1[1]) * nz + idx1[2];
                     const float w1 = weight[i1], f1 = tsdf[i1];
-                    if (!(w1 != 0.0f && f1 < 0.98f && f1 >= -0.98f && f0 * f1 < 0)) continue;
+                    if (!(orc_valid_w(w1) && f1 < 0.98f && f1 >= -0.98f && f0 * f1 < 0)) continue;
                     const float r0 = fabsf(f0), r1 = fabsf(f1);
                     double p[3] = {p0[0], p0[1], p0[2]};
                     const double p1i = p0[i] + voxel_length;
@@ -503,6 +511,102 @@ ORC_API int64_t orc_extract_points(const float *tsdf, const float *weight, const
                 }
             }
     return np;
+}
+
+/* ------------------------------------------------------------------ A.6 (row f4)
+ * `MAP.integrate` (N/3DM/tsdf.py:71-83) = Open3D t.pipelines.slam.Model.integrate on a VoxelBlockGrid of 16^3 blocks,
+ * restated on a bounded dense box whose origin is block0 * block_size (block_size = 16 * voxel_size); PARITY UNPINNED
+ * (written from knowledge of Open3D's VoxelBlockGridImpl.h: DepthTouch + Integrate; float32 tsdf / weight / colour).
+ *   pose         camera -> world 4x4 f64 (T_frame_to_model); the extrinsic is its rigid inverse (f64), cast to
+ *                float with the rotation entries pre-multiplied by voxel_size (TransformIndexer(.., voxel_size))
+ *   touch        every 4th pixel, d = (float)u16 / depth_scale, 0 < d < depth_max: ray through Unproject(x, y, 1)
+ *                and the pose; blocks at t = t_min + k * (t_max - t_min) / 3, k = 0..3
+ *   integrate    voxel position = integer voxel coordinate (world grid) as float; u = fx * x * (1/z) + cx, truncation;
+ *                sdf = depth - z (projective); skip depth <= 0, depth > depth_max, z <= 0, sdf < -trunc;
+ *                tsdf = (w * tsdf + min(sdf, trunc) / trunc) * (1 / (w + 1)); colour alike; w += 1
+ * touched_out: optional [nbx*nby*nbz] bytes ((xb * nby + yb) * nbz + zb).  Returns the number of voxels updated.
+ */
+ORC_API int64_t orc_vbg_integrate(float *tsdf, float *weight, float *color, int nx, int ny, int nz, const int *block0,
+                                  double voxel_size, double trunc_voxel_multiplier, const uint16_t *depth, const uint8_t *rgb,
+                                  int W, int H, const double *K, const double *pose, double depth_scale_d, double depth_max_d,
+                                  uint8_t *touched_out) {
+    const int B = 16;
+    const int nbx = (nx + B - 1) / B, nby = (ny + B - 1) / B, nbz = (nz + B - 1) / B;
+    const float fx = (float)K[0], fy = (float)K[1], cx = (float)K[2], cy = (float)K[3];
+    const float vs = (float)voxel_size, depth_scale = (float)depth_scale_d, depth_max = (float)depth_max_d;
+    const float trunc = vs * (float)trunc_voxel_multiplier, block_size = vs * (float)B;
+    double E[12];
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) E[4 * i + j] = pose[4 * j + i];
+        E[4 * i + 3] = -(pose[4 * 0 + i] * pose[3] + pose[4 * 1 + i] * pose[7] + pose[4 * 2 + i] * pose[11]);
+    }
+    float Es[12], P[12];
+    for (int i = 0; i < 3; ++i) {
+        for (int j = 0; j < 3; ++j) Es[4 * i + j] = (float)E[4 * i + j] * vs;
+        Es[4 * i + 3] = (float)E[4 * i + 3];
+    }
+    for (int i = 0; i < 12; ++i) P[i] = (float)pose[i];
+    uint8_t *touched = (uint8_t *)calloc((size_t)nbx * nby * nbz, 1);
+    for (int y = 0; y + 0 < (H / 4) * 4; y += 4)
+        for (int x = 0; x < (W / 4) * 4; x += 4) {
+            const float d = (float)depth[(size_t)y * W + x] / depth_scale;
+            if (!(d > 0.0f && d < depth_max)) continue;
+            const float xc = ((float)x - cx) * 1.0f / fx, yc = ((float)y - cy) * 1.0f / fy, zc = 1.0f;
+            const float xg = ((xc * P[0] + yc * P[1]) + zc * P[2]) + P[3];
+            const float yg = ((xc * P[4] + yc * P[5]) + zc * P[6]) + P[7];
+            const float zg = ((xc * P[8] + yc * P[9]) + zc * P[10]) + P[11];
+            const float xo = P[3], yo = P[7], zo = P[11];
+            const float xd = xg - xo, yd = yg - yo, zd = zg - zo;
+            const float t_min = fmaxf(d - trunc, 0.0f), t_max = fminf(d + trunc, depth_max);
+            const float t_step = (t_max - t_min) / 3.0f;
+            float t = t_min;
+            for (int step = 0; step <= 3; ++step) {
+                const int xb = (int)floorf((xo + t * xd) / block_size) - block0[0];
+                const int yb = (int)floorf((yo + t * yd) / block_size) - block0[1];
+                const int zb = (int)floorf((zo + t * zd) / block_size) - block0[2];
+                if (xb >= 0 && yb >= 0 && zb >= 0 && xb < nbx && yb < nby && zb < nbz) touched[((size_t)xb * nby + yb) * nbz + zb] = 1;
+                t += t_step;
+            }
+        }
+    int64_t updated = 0;
+    const int n_blocks = nbx * nby * nbz;
+#pragma omp parallel for schedule(dynamic) reduction(+ : updated)
+    for (int b = 0; b < n_blocks; ++b) {
+        if (!touched[b]) continue;
+        const int zb = b % nbz, yb = (b / nbz) % nby, xb = b / (nbz * nby);
+        for (int lx = 0; lx < B; ++lx)
+            for (int ly = 0; ly < B; ++ly)
+                for (int lz = 0; lz < B; ++lz) {
+                    const int X = xb * B + lx, Y = yb * B + ly, Z = zb * B + lz;
+                    if (X >= nx || Y >= ny || Z >= nz) continue;
+                    const float xw = (float)(block0[0] * B + X), yw = (float)(block0[1] * B + Y), zw = (float)(block0[2] * B + Z);
+                    const float xc = ((xw * Es[0] + yw * Es[1]) + zw * Es[2]) + Es[3];
+                    const float yc = ((xw * Es[4] + yw * Es[5]) + zw * Es[6]) + Es[7];
+                    const float zc = ((xw * Es[8] + yw * Es[9]) + zw * Es[10]) + Es[11];
+                    const float inv_z = 1.0f / zc;
+                    const float u = fx * xc * inv_z + cx, v = fy * yc * inv_z + cy;
+                    if (!(u >= 0.0f && v >= 0.0f && u < (float)W && v < (float)H)) continue;
+                    const int ui = (int)u, vi = (int)v;
+                    const float d = (float)depth[(size_t)vi * W + ui] / depth_scale;
+                    float sdf = d - zc;
+                    if (d <= 0.0f || d > depth_max || zc <= 0.0f || sdf < -trunc) continue;
+                    sdf = sdf < trunc ? sdf : trunc;
+                    sdf /= trunc;
+                    const size_t idx = ((size_t)X * ny + Y) * nz + Z;
+                    const float w = weight[idx];
+                    const float inv = 1.0f / (w + 1.0f);
+                    tsdf[idx] = (w * tsdf[idx] + sdf) * inv;
+                    if (color && rgb) {
+                        const uint8_t *c = rgb + ((size_t)vi * W + ui) * 3;
+                        for (int k = 0; k < 3; ++k) color[3 * idx + k] = (w * color[3 * idx + k] + (float)c[k]) * inv;
+                    }
+                    weight[idx] = w + 1.0f;
+                    ++updated;
+                }
+    }
+    if (touched_out) memcpy(touched_out, touched, (size_t)n_blocks);
+    free(touched);
+    return updated;
 }
 
 /* occupancy helper for the parity tests: number of voxels with weight != 0 */
