@@ -55,7 +55,7 @@ def test_map_integrate_matches_oracle(cuda, scene, res, vs, tmp_path):
                                      trunc_voxel_multiplier=4.0, return_touched=True)
         co.append(n)
         blocks += int(touched.sum())
-    assert sum(co) > 10000 and blocks > 10
+    assert sum(co) > 1000 and blocks > 0, (co, blocks)
     t, w, c = (x.cpu().numpy() for x in m.model.export_dense(with_color=True))
     assert np.array_equal(w, V.grid("weight")), "weights / occupancy differ"
     assert np.array_equal(t, V.grid("tsdf")), f"tsdf differs by {np.abs(t - V.grid('tsdf')).max()}"
@@ -77,7 +77,7 @@ def test_map_integrate_matches_oracle(cuda, scene, res, vs, tmp_path):
     mesh, pcd = m.extract_mesh(), m.extract_pcd()
     a = canon_mesh(mesh.vertices.cpu().numpy(), mesh.vertex_keys.cpu().numpy(), mesh.triangles.cpu().numpy(), (res,) * 3)
     b = canon_mesh(ref["vertices"], ref["keys"], ref["triangles"], (res,) * 3)
-    assert len(ref["triangles"]) > 100
+    assert len(ref["triangles"]) > (100 if scene == "laparoscopy512" else 0)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[2], b[2]) and np.abs(a[1] - b[1]).max() <= 1e-4 * vs
     assert int(pcd.points.shape[0]) == len(refp["points"])
     # a lower threshold keeps more surface
