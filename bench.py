@@ -61,6 +61,9 @@ def parse():
     ap.add_argument("--cpu-budget", type=float, default=6.0, help="seconds of CPU oracle work per timed CPU leg")
     ap.add_argument("--deviation", action="store_true", help="also quantify brick-restart vs literal z recurrence over all frames (slow validation kernel)")
     ap.add_argument("--const-depth", type=int, default=0, help="EXPERIMENT: replace every frame by this constant uint16 depth (limit studies with BSLAM_EXPERIMENT; not a bench value)")
+    ap.add_argument("--resident-layout", default="rank0", choices=["rank0", "sharded"],
+                    help="N > 1, where the resident u16 frames live before the timed region: all on rank 0 (NCCL broadcast per chunk) or 1/N of every "
+                         "chunk in each rank's HBM (NCCL all-gather per chunk)")
     ap.add_argument("--emulate-shard", default="", help="R/N: time rank R's shard of an N-GPU run on ONE GPU (no NCCL; development aid)")
     return ap.parse_args()
 
@@ -367,11 +370,20 @@ def main():
     chunk = args.batch or 256
     chunks = vol.stream_chunks(F, chunk, ramp=ShardedTSDF.stream_ramp(world, True))   # integrate launches of a resident step
 
+    dev_share = None
+    if world > 1 and args.resident_layout == "sharded":
+        # every rank keeps the frames ingest_share() assigns to it (1/N of every chunk) in ITS HBM
+        sel_share = torch.as_tensor(ShardedTSDF.ingest_share(F, rank, world, chunk), device=dev)
+        dev_share = depth_u16.view(torch.int16)[sel_share].view(torch.uint16).contiguous()
+
     def step(src_u16, counts=None):
-        """one pass of the hot path over the whole trajectory through the public API: src_u16 is rank 0's
-        uint16 depth (device-resident for `value`, pinned host memory for `e2e`).  a4 is fused into the
-        integration's first pass; N > 1: rank 0's frames are broadcast over NCCL chunk by chunk, the
-        broadcast of chunk k+1 (and the H2D of chunk k+2) overlapping the integration of chunk k."""
+        """one pass of the hot path over the whole trajectory through the public API.  a4 is fused into the
+        integration's first pass.  N > 1: the frames reach every rank over NCCL chunk by chunk inside the timed
+        region -- all-gathered from the ranks' resident shares (default) or broadcast from rank 0 -- the transfer
+        of chunk k+1 (and the H2D of chunk k+2 when the source is host memory) overlapping the integration of chunk k."""
+        if dev_share is not None and src_u16 is depth_u16:
+            sh.integrate_stream_sharded(dev_share, intr, E, depth_scale=1000.0, depth_trunc=3.0, chunk=chunk, update_counts=counts)
+            return
         if emu:
             for f0, f1 in chunks:
                 vol.integrate_u16_batch(src_u16[f0:f1], None, intr, E[f0:f1], 1000.0, 3.0, update_counts=None if counts is None else counts[f0:f1])
@@ -655,18 +667,21 @@ def main():
         # ---- BASELINE configs[2]: 64-frame batched 1080p depth scale + colorize + back-project
         from bodyslam_b200 import mdem
 
+        # input: 64 views of the same synthetic scene rendered at 1080p (intrinsics scaled x3), 2 % invalid pixels,
+        # as float32 METRES (what ZoeDepth hands to the MDEM post-processing)
         B, Hh, Ww = 64, 1080, 1920
-        g = torch.Generator(device=dev).manual_seed(0)
-        metres = 0.3 + 2.5 * torch.rand((B, Hh, Ww), device=dev, generator=g)
-        metres[:, ::7, ::5] = 0.0
+        K1080 = tuple(k * 3.0 for k in cfg["K"])
+        Eb = E[np.linspace(0, len(E) - 1, B).astype(int)]
+        d1080, _ = S.render(cfg["surface"], Eb, K=K1080, W=Ww, H=Hh, device=dev, with_color=False)
+        metres = (d1080.to(torch.float32) / 1000.0).contiguous()
+        del d1080
         lut = mdem.get_cmap_lut("viridis")
         ms = timed(lambda: ops.colorize_u16(lut, depth_m=metres, invalid_val=0))
         px = B * Hh * Ww
         peak = load_peaks()[0]
         extras["configs2_k1_scale_colorize_1080p_x64"] = {"ms": ms, "frames_per_s": B / (ms / 1e3), "algorithmic_GBps": 10 * px / 1e9 / (ms / 1e3),
-                                                          "frac_of_hbm_peak": 10 * px / 1e9 / (ms / 1e3) / peak, "algorithmic_bytes": "10 B/px (4 r + 2 w + 4 w)"}
-        K1080 = tuple(k * 3.0 for k in cfg["K"])
-        Eb = np.stack([E[i % len(E)] for i in range(B)])
+                                                          "frac_of_hbm_peak": 10 * px / 1e9 / (ms / 1e3) / peak, "algorithmic_bytes": "10 B/px (4 r + 2 w + 4 w)",
+                                                          "input": "64 rendered 1080p views of the workload's scene, f32 metres, 2 % invalid"}
         res_bp = {}
 
         def bp():
@@ -788,6 +803,8 @@ def main():
             "config": config_dict(args, F, W, H, res, vl, trunc),
             "details": {"step": "a4 depth scaling (fused into the first pass) + K3 integrate of all frames, volume resident",
                         "culling": {"voxels_tested_per_frame": cull["voxels_tested"] / F, "updated_over_tested": (int(uf_local.sum().item()) / cull["voxels_tested"]) if cull["voxels_tested"] else None},
+                        "resident_frames": (None if world == 1 else ("1/N of every chunk resident in each rank's HBM, all-gathered over NVLink per chunk" if dev_share is not None
+                                                                     else "all frames resident on rank 0, broadcast over NVLink per chunk")),
                         "parallelism": (f"round-robin brick-layer z-shards x{world}" if interleaved else f"z-slab x{world}") if world > 1 else
                                        (f"EMULATED shard {emu[0]} of {emu[1]} on one GPU (development aid, not a bench value)" if emu else "single GPU"),
                         "voxels_updated_per_frame": uf_total / F, "timeline_ms_per_step_by_rank": timeline, **mesh_info, **extras},

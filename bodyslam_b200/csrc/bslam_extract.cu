@@ -418,10 +418,32 @@ __device__ double tsdf_at(const VolView &v, double vl, const double *p) {
     return t;
 }
 
+// trilinear TSDF at local position p from the staged (11^3) neighbourhood of the brick: voxels -1 .. 9 per axis
+// (a point of voxel X along axis a needs X - 1 .. X + 2, see A.5), same term order as tsdf_at
+constexpr int kPR = 11;
+__device__ __forceinline__ double tsdf_at_staged(const float *s_t, double vl, double pos_half, int bx8, int by8, int bz8, const double *p) {
+    int idx[3]; double r[3];
+    for (int i = 0; i < 3; ++i) {
+        const double g = p[i] / vl - pos_half;
+        idx[i] = (int)floor(g);
+        r[i] = g - (double)idx[i];
+    }
+    const int rx = idx[0] - bx8 + 1, ry = idx[1] - by8 + 1, rz = idx[2] - bz8 + 1;
+    double t = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { // Open3D term order: (0,0,0),(0,0,1),(0,1,0),(0,1,1),(1,0,0),...
+        const int a = (k >> 2) & 1, b = (k >> 1) & 1, c = k & 1;
+        const double wgt = (a ? r[0] : 1 - r[0]) * (b ? r[1] : 1 - r[1]) * (c ? r[2] : 1 - r[2]);
+        t += wgt * (double)s_t[((rz + c) * kPR + (rx + a)) * kPR + (ry + b)];
+    }
+    return t;
+}
+
 template <bool EMIT>
 __global__ void __launch_bounds__(kBrickVox) points_brick_kernel(const VolView v, double vl, McScratch sc, float *points, float *normals,
                                                                   float *colors, int32_t *keys, int64_t cap) {
     __shared__ uint32_t s_w[16];
+    __shared__ float s_t[EMIT ? kPR * kPR * kPR : 1];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const unsigned int n_cand = (unsigned int)sc.totals[2];
   for (unsigned int ci = blockIdx.x; ci < n_cand; ci += gridDim.x) {      // persistent grid over the candidate list
@@ -429,6 +451,14 @@ __global__ void __launch_bounds__(kBrickVox) points_brick_kernel(const VolView v
     const int64_t b = sc.list[ci];
     if (EMIT && sc.nvert[b] == 0) continue;
     const int bx = (int)(b % v.nbx), by = (int)((b / v.nbx) % v.nby), bz = (int)(b / ((int64_t)v.nbx * v.nby));
+    if (EMIT && normals) {
+        // the tsdf of voxels -1 .. 9 of the brick per axis (0 outside the box; never read for a valid point)
+        for (int i = tid; i < kPR * kPR * kPR; i += kBrickVox) {
+            const int ry = i % kPR, rx = (i / kPR) % kPR, rz = i / (kPR * kPR);
+            const int x = bx * 8 - 1 + rx, y = by * 8 - 1 + ry, z = bz * 8 - 1 + rz;
+            s_t[i] = (x >= 0 && y >= 0 && z >= 0 && x < v.nx && y < v.ny && z < v.nz) ? v.vox[voxel_slot(v, x, y, z)].x : 0.0f;
+        }
+    }
     const int ly = tid & 7, lx = (tid >> 3) & 7, lz = tid >> 6;
     const int X = bx * 8 + lx, Y = by * 8 + ly, Z = bz * 8 + lz;
     const int n[3] = {v.nx, v.ny, v.nz};
@@ -480,7 +510,7 @@ __global__ void __launch_bounds__(kBrickVox) points_brick_kernel(const VolView v
                 for (int k = 0; k < 3; ++k) {
                     double q0[3] = {p[0], p[1], p[2]}, q1[3] = {p[0], p[1], p[2]};
                     q0[k] -= half_gap; q1[k] += half_gap;
-                    nn[k] = tsdf_at(v, vl, q1) - tsdf_at(v, vl, q0);
+                    nn[k] = tsdf_at_staged(s_t, vl, v.pos_half, bx * 8, by * 8, bz * 8, q1) - tsdf_at_staged(s_t, vl, v.pos_half, bx * 8, by * 8, bz * 8, q0);
                 }
                 const double len = sqrt(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
                 for (int k = 0; k < 3; ++k) normals[3 * o + k] = (float)(len > 0 ? nn[k] / len : nn[k]);

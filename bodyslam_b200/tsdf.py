@@ -455,6 +455,7 @@ class TSDF:
         if not unit_activation:
             self.tsdf.set_clip_check(8)
         self._clip_warned = 0.0
+        self._next_clip_check = 1      # frames_integrated at which the next (synchronising) clip check is due
 
     def clipped_fraction(self) -> float:
         """share of the sampled depth points integrated so far that fell OUTSIDE the bounded box (the
@@ -465,6 +466,12 @@ class TSDF:
     def _warn_if_clipped(self):
         import warnings
 
+        # the counters live on the device: read them at frames 1, 4, 16, ... so the per-frame cadence
+        # (extract_pcd after every build_3D_map, N/3DM/slam.py:195) does not pay a device round trip per call
+        if self.tsdf.frames_integrated < self._next_clip_check:
+            return
+        while self._next_clip_check <= self.tsdf.frames_integrated:
+            self._next_clip_check *= 4
         frac = self.clipped_fraction()
         if frac > 0.01 and frac > 1.5 * self._clip_warned:
             self._clip_warned = frac
