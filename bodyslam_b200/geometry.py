@@ -18,6 +18,27 @@ def to_numpy(x):
     return np.asarray(x)
 
 
+def inverse4x4(m):
+    """General 4x4 inverse by cofactors, row-major float64 -- the formula Eigen's `Matrix4d::inverse()` evaluates
+    (Open3D: `extrinsic.inverse()` in CreateFromDepthImage / ScalableTSDFVolume::Integrate), so that the camera
+    pose handed to the kernels has Open3D's rounding rather than LAPACK's.  Accepts [..., 4, 4]."""
+    a = np.asarray(m, dtype=np.float64)
+    flat = a.reshape(-1, 4, 4)
+    out = np.empty_like(flat)
+    for n, M in enumerate(flat):
+        c = np.empty((4, 4))
+        for i in range(4):
+            for j in range(4):
+                minor = np.delete(np.delete(M, j, axis=0), i, axis=1)
+                d3 = (minor[0, 0] * (minor[1, 1] * minor[2, 2] - minor[1, 2] * minor[2, 1])
+                      - minor[0, 1] * (minor[1, 0] * minor[2, 2] - minor[1, 2] * minor[2, 0])
+                      + minor[0, 2] * (minor[1, 0] * minor[2, 1] - minor[1, 1] * minor[2, 0]))
+                c[i, j] = -d3 if (i + j) & 1 else d3
+        det = M[0, 0] * c[0, 0] + M[0, 1] * c[1, 0] + M[0, 2] * c[2, 0] + M[0, 3] * c[3, 0]
+        out[n] = c / det
+    return out.reshape(a.shape)
+
+
 class PinholeCameraIntrinsic:
     """Open3D `camera.PinholeCameraIntrinsic` look-alike (N/3DM/slam_utils.py:48-68)."""
 

@@ -128,6 +128,13 @@ def colorize_cuda(value, vmin=None, vmax=None, cmap='gray_r', invalid_val=-99, i
         name = str(v.dtype)
     if name not in ("uint16", "uint8", "int16", "int32", "int64", "float32", "float64"):
         raise RuntimeError(f"[colorize] Unsupported image format. (dtype {name})")
+    if v.ndim < 2:
+        # a single row / a single pixel after the reference's squeeze(): colour it as a one-row image and give the
+        # result the squeezed shape + (4,), like `cmapper(value, bytes=True)` does
+        shape = tuple(v.shape)
+        mask1 = None if invalid_mask is None else to_numpy(invalid_mask).reshape(1, -1)
+        out = colorize_cuda(v.reshape(1, -1), vmin, vmax, cmap, invalid_val, mask1, background_color, gamma_corrected, value_transform, device)
+        return out.reshape(shape + (4,))
     lut = get_cmap_lut(cmap)
     bg = np.asarray(list(background_color) + [255] * (4 - len(background_color)), dtype=np.uint8)
     if gamma_corrected:

@@ -11,7 +11,7 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from .geometry import to_numpy
+from .geometry import inverse4x4, to_numpy
 
 
 def _device(device=None):
@@ -221,7 +221,7 @@ def backproject(depth, K, extrinsic=None, color=None, stride=1, valid_only=True,
     E = np.eye(4)[None].repeat(B, 0) if extrinsic is None else np.asarray(to_numpy(extrinsic), dtype=np.float64).reshape(-1, 4, 4)
     if E.shape[0] == 1 and B > 1:
         E = E.repeat(B, 0)
-    M = np.ascontiguousarray(np.linalg.inv(E)[:, :3, :].reshape(B, 12), dtype=np.float32)
+    M = np.ascontiguousarray(inverse4x4(E)[:, :3, :].reshape(B, 12), dtype=np.float32)   # Eigen's cofactor inverse, like Open3D
     Kf = np.ascontiguousarray(K, dtype=np.float32)
     c8 = None
     if color is not None:

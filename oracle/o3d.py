@@ -94,7 +94,9 @@ def backproject(depth_f32, K, extrinsic=None, rgb=None, stride=1, valid_only=Tru
     H, W = d.shape
     Kd = np.ascontiguousarray(K, dtype=np.float64)
     E = np.eye(4) if extrinsic is None else np.asarray(extrinsic, dtype=np.float64)
-    M = np.ascontiguousarray(np.linalg.inv(E))
+    M = np.zeros(16)
+    lib().orc_invert4x4(_ptr(np.ascontiguousarray(E)), _ptr(M))      # Eigen's 4x4 inverse is the cofactor formula
+    M = M.reshape(4, 4)
     rows = ((H + stride - 1) // stride) * ((W + stride - 1) // stride)
     xyz = np.empty((rows, 3), np.float64)
     c = None
