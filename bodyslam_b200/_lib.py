@@ -38,6 +38,8 @@ _SIGNATURES = {
     "bslam_tsdf_copy": (C.c_int, [_p, _p, _p]),
     "bslam_tsdf_integrate": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_int, _p, _p, C.c_int, _p, C.c_int, _p]),
     "bslam_tsdf_integrate_u16": (C.c_int, [_p, _p, C.c_float, C.c_float, _p, _p, C.c_int, C.c_int, C.c_int, _p, _p, _p, _p]),
+    "bslam_tsdf_prepare_u16": (C.c_int, [_p, _p, C.c_float, C.c_float, _p, C.c_int, C.c_int, C.c_int, _p, _p, _p]),
+    "bslam_tsdf_integrate_prepared": (C.c_int, [_p, _p, _p, _p]),
     "bslam_tsdf_set_z_interleave": (C.c_int, [_p, C.c_int]),
     "bslam_tsdf_layout": (C.c_int, [_p, _p]),
     "bslam_tsdf_set_batch": (C.c_int, [_p, C.c_int]),

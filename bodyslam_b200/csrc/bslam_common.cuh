@@ -128,11 +128,18 @@ struct bslam_volume {
     int batch; // frames per integrate launch (0 = default)
     int prof_enabled, prof_n;
     int zpw;                                  // z layers per integrate warp (0 = auto by shard size)
+    // two-stream pipeline (bslam_tsdf_prepare_u16 / bslam_tsdf_integrate_prepared): second scratch buffer, two slots
+    void *int_scratch2;
+    void *slot_bp[2];                         // host copies of the prepared launches' parameters (BatchP)
+    cudaEvent_t slot_ready[2], slot_free[2];
+    int slot_used[2], slot_prof[2], slot_tiles[2][2];
+    int prep_head, prep_tail, prep_pending;
     int clip_stride;                          // dense mode: sampling stride of the out-of-box point count (0 = off)
     int z_total;                              // planes of the whole grid when this box is a z-shard (clip check)
     static constexpr int kProfPairs = 1024;   // integrate launches timed per bslam_tsdf_profile_read
     static constexpr int kProfStages = 3;     // depth statistics (+ fused a4) | unit marks + culls + order | brick integrate
-    cudaEvent_t prof_ev[(kProfStages + 1) * kProfPairs];
+    static constexpr int kProfEvents = 5;     // per launch: prepare start / after statistics / prepare end | integrate start / end
+    cudaEvent_t prof_ev[kProfEvents * kProfPairs];
     double prof_ms_accum[kProfStages];
     long long prof_launches_accum;
 };

@@ -115,16 +115,18 @@ def colorize(value, vmin=None, vmax=None, cmap='gray_r', invalid_val=-99, invali
 
 
 def colorize_cuda(value, vmin=None, vmax=None, cmap='gray_r', invalid_val=-99, invalid_mask=None,
-                  background_color=(128, 128, 128, 255), gamma_corrected=False, value_transform=None, device=None):
+                  background_color=(128, 128, 128, 255), gamma_corrected=False, value_transform=None, device=None, _squeeze=True):
     """`colorize` that leaves the RGBA image on the device ([H,W,4] or [B,H,W,4] uint8 CUDA tensor)."""
     torch = _lib.require_cuda()
     if hasattr(value, "detach"):
         v = value.detach()
-        while v.dim() > 2 and 1 in v.shape:
+        while _squeeze and v.dim() > 2 and 1 in v.shape:
             v = v.squeeze()
         name = str(v.dtype).replace("torch.", "")
     else:
-        v = np.asarray(value).squeeze()
+        v = np.asarray(value)
+        if _squeeze:
+            v = v.squeeze()
         name = str(v.dtype)
     if name not in ("uint16", "uint8", "int16", "int32", "int64", "float32", "float64"):
         raise RuntimeError(f"[colorize] Unsupported image format. (dtype {name})")
@@ -133,7 +135,8 @@ def colorize_cuda(value, vmin=None, vmax=None, cmap='gray_r', invalid_val=-99, i
         # result the squeezed shape + (4,), like `cmapper(value, bytes=True)` does
         shape = tuple(v.shape)
         mask1 = None if invalid_mask is None else to_numpy(invalid_mask).reshape(1, -1)
-        out = colorize_cuda(v.reshape(1, -1), vmin, vmax, cmap, invalid_val, mask1, background_color, gamma_corrected, value_transform, device)
+        out = colorize_cuda(v.reshape(1, -1), vmin, vmax, cmap, invalid_val, mask1, background_color, gamma_corrected, value_transform, device,
+                            _squeeze=False)
         return out.reshape(shape + (4,))
     lut = get_cmap_lut(cmap)
     bg = np.asarray(list(background_color) + [255] * (4 - len(background_color)), dtype=np.uint8)

@@ -315,9 +315,9 @@ class ShardedTSDF:
         if self.world_size == 1:
             chunks = vol.stream_chunks(F, chunk, ramp=self.stream_ramp(1, on_dev))
             if on_dev:
-                for f0, f1 in chunks:
-                    vol.integrate_u16_batch(depth_u16[f0:f1], None, intrinsic, E[f0:f1], depth_scale, depth_trunc,
-                                            update_counts=None if update_counts is None else update_counts[f0:f1])
+                if vol.color:
+                    raise RuntimeError("integrate_stream: colour volumes are not streamed yet (use integrate_batch / integrate_host)")
+                vol.integrate_u16_chunks(depth_u16, None, intrinsic, E, chunks, depth_scale, depth_trunc, update_counts)
             else:
                 vol.integrate_host(depth_u16, None, intrinsic, E, depth_scale, depth_trunc, chunk, update_counts)
             return
@@ -363,15 +363,22 @@ class ShardedTSDF:
                     # stream that is current at the call); NCCL has no 16-bit integer type: ship bytes
                     return dist.broadcast(u16.view(torch.uint8), src, group=self.group, async_op=True)
 
+            vol.prep_stream().wait_stream(main)
+
+            def prep(k):     # conversion + statistics + culling of chunk k on the side stream, once its frames have arrived
+                f0, f1 = chunks[k]
+                vol.prepare_u16(bufs.pop(k), intrinsic, E[f0:f1], stage[k % 3][1], depth_scale, depth_trunc, wait=works.pop(k).wait)
+
             works = {0: issue(0)}
             if len(chunks) > 1:
                 works[1] = issue(1)
+            prep(0)
             for k, (f0, f1) in enumerate(chunks):
                 if k + 2 < len(chunks):
                     works[k + 2] = issue(k + 2)
-                works.pop(k).wait()                                # current stream waits for chunk k
-                vol.integrate_u16_batch(bufs.pop(k), None, intrinsic, E[f0:f1], depth_scale, depth_trunc, scratch=stage[k % 3][1],
-                                        update_counts=None if update_counts is None else update_counts[f0:f1])
+                if k + 1 < len(chunks):
+                    prep(k + 1)                                    # overlaps the integration of chunk k
+                vol.integrate_prepared(None, None if update_counts is None else update_counts[f0:f1])
                 free[k % 3] = torch.cuda.Event()
                 free[k % 3].record(main)
 
@@ -453,16 +460,24 @@ class ShardedTSDF:
                                 works.append(dist.broadcast(u8[q0 - f0:q1 - f0], q, group=self.group, async_op=True))
                 return works
 
+            vol.prep_stream().wait_stream(main)
+
+            def prep(k):
+                f0, f1 = chunks[k]
+                ws = pending.pop(k)
+                vol.prepare_u16(stage[k % 3][0][:f1 - f0], intrinsic, E[f0:f1], stage[k % 3][1], depth_scale, depth_trunc,
+                                wait=lambda: [w.wait() for w in ws])
+
             pending = {0: issue(0)}
             if len(chunks) > 1:
                 pending[1] = issue(1)
+            prep(0)
             for k, (f0, f1) in enumerate(chunks):
                 if k + 2 < len(chunks):
                     pending[k + 2] = issue(k + 2)
-                for w in pending.pop(k):
-                    w.wait()                                         # current stream waits for chunk k
-                vol.integrate_u16_batch(stage[k % 3][0][:f1 - f0], None, intrinsic, E[f0:f1], depth_scale, depth_trunc,
-                                        scratch=stage[k % 3][1], update_counts=None if update_counts is None else update_counts[f0:f1])
+                if k + 1 < len(chunks):
+                    prep(k + 1)                                      # overlaps the integration of chunk k
+                vol.integrate_prepared(None, None if update_counts is None else update_counts[f0:f1])
                 free[k % 3] = torch.cuda.Event()
                 free[k % 3].record(main)
 

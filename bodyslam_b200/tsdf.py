@@ -200,6 +200,75 @@ class DenseTSDFVolume:
         self.frames_integrated += F
         return scratch
 
+    # ------------------------------------------------------------------ two-stream launch pipeline
+    def prep_stream(self):
+        """side stream for the part of a launch that does not touch the volume (conversion, statistics, culling)"""
+        torch = _lib.require_cuda()
+        if getattr(self, "_prep_stream", None) is None:
+            self._prep_stream = torch.cuda.Stream(self.device)
+        return self._prep_stream
+
+    def prepare_u16(self, depth_u16, intrinsic, extrinsics, scratch, depth_scale: float = 1000.0, depth_trunc: float = 3.0, wait=None):
+        """enqueue the preparation of one launch (<= 256 frames; see bslam_tsdf_prepare_u16) on the side stream.
+        `wait`: optional callable run with the side stream current (e.g. `work.wait` of an NCCL transfer or
+        `lambda: stream.wait_event(ev)`) -- what the frames' arrival is ordered by.  Up to two launches ahead."""
+        torch = _lib.require_cuda()
+        W, H, fx, fy, cx, cy = intrinsic_params(intrinsic)
+        if depth_u16.dim() == 2:
+            depth_u16 = depth_u16.unsqueeze(0)
+        if (not depth_u16.is_cuda or depth_u16.dtype != torch.uint16 or depth_u16.dim() != 3 or depth_u16.shape[1] != H or depth_u16.shape[2] != W
+                or not depth_u16.is_contiguous()):
+            raise RuntimeError("[DenseTSDFVolume::Integrate] Unsupported image format.")
+        F = depth_u16.shape[0]
+        E = np.ascontiguousarray(np.asarray(to_numpy(extrinsics), dtype=np.float64).reshape(-1, 16))
+        if E.shape[0] != F:
+            raise RuntimeError(f"prepare_u16: {F} frames but {E.shape[0]} extrinsics")
+        if scratch is None or scratch.numel() < F * H * W:
+            raise RuntimeError("prepare_u16: the f32 scratch must hold the launch's frames")
+        K = np.array([fx, fy, cx, cy], dtype=np.float64)
+        ps = self.prep_stream()
+        with torch.cuda.device(self.device), torch.cuda.stream(ps):
+            if wait is not None:
+                wait()
+            _lib.check(self._L.bslam_tsdf_prepare_u16(self._h, _lib.ptr(depth_u16), float(depth_scale), float(depth_trunc or 0.0), _lib.ptr(scratch),
+                                                      F, H, W, _lib.ptr(K), _lib.ptr(E), C.c_void_p(ps.cuda_stream)))
+        self._prepared = getattr(self, "_prepared", [])
+        self._prepared.append((F, depth_u16, scratch))      # keep the buffers alive until the launch is integrated
+
+    def integrate_prepared(self, color=None, update_counts=None):
+        """enqueue the integration of the oldest prepared launch on the current stream"""
+        torch = _lib.require_cuda()
+        F, _, _ = self._prepared.pop(0)
+        if self.color and color is None:
+            raise RuntimeError("[DenseTSDFVolume::Integrate] Unsupported image format.")
+        with torch.cuda.device(self.device):
+            _lib.check(self._L.bslam_tsdf_integrate_prepared(self._h, _lib.ptr(color) if self.color else None, _lib.ptr(update_counts),
+                                                             _lib.stream_ptr(self.device)))
+        self.frames_integrated += F
+
+    def integrate_u16_chunks(self, depth_u16, color, intrinsic, extrinsics, chunks, depth_scale: float = 1000.0, depth_trunc: float = 3.0,
+                             update_counts=None):
+        """device-resident uint16 frames, launch after launch through the two-stream pipeline: chunk k+1 is converted and
+        culled on the side stream while chunk k integrates (`chunks`: [(f0, f1)], each <= 256 frames)."""
+        torch = _lib.require_cuda()
+        E = np.asarray(to_numpy(extrinsics), dtype=np.float64).reshape(-1, 4, 4)
+        if not chunks:
+            return
+        H, W = depth_u16.shape[1], depth_u16.shape[2]
+        stage = self._staging(max(f1 - f0 for f0, f1 in chunks), H, W, False, count=3)
+        main = torch.cuda.current_stream(self.device)
+        self.prep_stream().wait_stream(main)             # the frames (and earlier launches) are ordered by the current stream
+
+        def prep(k):
+            f0, f1 = chunks[k]
+            self.prepare_u16(depth_u16[f0:f1], intrinsic, E[f0:f1], stage[k % 3][1], depth_scale, depth_trunc)
+
+        prep(0)
+        for k, (f0, f1) in enumerate(chunks):
+            if k + 1 < len(chunks):
+                prep(k + 1)
+            self.integrate_prepared(None if color is None else color[f0:f1], None if update_counts is None else update_counts[f0:f1])
+
     @staticmethod
     def stream_chunks(F: int, chunk: int = 256, ramp=(32, 64, 128), multiple_of: int = 1):
         """[(f0, f1)] for streamed integration: a short ramp first, so that the compute stream starts
@@ -225,7 +294,7 @@ class DenseTSDFVolume:
                     f += m
         return out
 
-    def _staging(self, n, H, W, use_color, count=2):
+    def _staging(self, n, H, W, use_color, count=3):
         torch = _lib.require_cuda()
         key = (n, H, W, use_color, count)
         if getattr(self, "_stage_key", None) != key:
@@ -273,24 +342,44 @@ class DenseTSDFVolume:
                 self._copy_stream = torch.cuda.Stream(dev)
             cs = self._copy_stream
             chunks = self.stream_chunks(F, chunk)
-            stage = self._staging(max(f1 - f0 for f0, f1 in chunks), H, W, use_color)
+            stage = self._staging(max(f1 - f0 for f0, f1 in chunks), H, W, use_color, count=3)
             free = self._stage_free  # event: the compute stream is done with staging buffer i
-            for k, (f0, f1) in enumerate(chunks):
+            ps = self.prep_stream()
+            ps.wait_stream(main)
+            copied = {}
+
+            def copy(k):                 # H2D of chunk k on the copy stream
+                f0, f1 = chunks[k]
                 m = f1 - f0
-                u16, f32, col = stage[k & 1]
+                u16, _, col = stage[k % 3]
                 with torch.cuda.stream(cs):
-                    if free[k & 1] is not None:
-                        cs.wait_event(free[k & 1])
+                    if free[k % 3] is not None:
+                        cs.wait_event(free[k % 3])
                     u16[:m].copy_(depth_u16[f0:f1], non_blocking=True)
                     if use_color:
                         col[:m].copy_(color[f0:f1], non_blocking=True)
-                    copied = torch.cuda.Event()
-                    copied.record(cs)
-                main.wait_event(copied)
-                self.integrate_u16_batch(u16[:m], col[:m] if use_color else None, intrinsic, E[f0:f1], depth_scale, depth_trunc,
-                                         scratch=f32, update_counts=None if update_counts is None else update_counts[f0:f1])
-                free[k & 1] = torch.cuda.Event()
-                free[k & 1].record(main)
+                    copied[k] = torch.cuda.Event()
+                    copied[k].record(cs)
+
+            def prep(k):                 # conversion + statistics + culling of chunk k on the side stream
+                f0, f1 = chunks[k]
+                ev = copied.pop(k)
+                self.prepare_u16(stage[k % 3][0][:f1 - f0], intrinsic, E[f0:f1], stage[k % 3][1], depth_scale, depth_trunc,
+                                 wait=lambda: ps.wait_event(ev))
+
+            copy(0)
+            if len(chunks) > 1:
+                copy(1)
+            prep(0)
+            for k, (f0, f1) in enumerate(chunks):
+                if k + 2 < len(chunks):
+                    copy(k + 2)
+                if k + 1 < len(chunks):
+                    prep(k + 1)
+                col = stage[k % 3][2]
+                self.integrate_prepared(col[:f1 - f0] if use_color else None, None if update_counts is None else update_counts[f0:f1])
+                free[k % 3] = torch.cuda.Event()
+                free[k % 3].record(main)
 
     def count_updates(self, depth, intrinsic, extrinsics, zmarch: int = _lib.ZMARCH_BRICK):
         """U_f of SURVEY.md 8(d): voxels each frame WOULD update (volume untouched) -> i64 [F]."""

@@ -189,6 +189,21 @@ BSLAM_API int bslam_tsdf_integrate_u16(bslam_volume *vol, const uint16_t *d_dept
                                        int F, int H, int W, const double *h_K, const double *h_extrinsics,
                                        unsigned long long *d_update_counts, bslam_stream_t stream);
 
+/*
+ * The same launch in two halves, for callers that stream chunk after chunk (update_map_after_pg-style replays):
+ * bslam_tsdf_prepare_u16 enqueues everything that does not touch the volume -- depth conversion + tile statistics,
+ * unit marks, culling, claim order -- for F <= BSLAM_MAX_BATCH frames on `prep_stream`;
+ * bslam_tsdf_integrate_prepared enqueues the integration of the OLDEST prepared launch on `stream` (it waits for
+ * the preparation through an event; no host synchronisation).  Up to two launches may be prepared ahead, so that the
+ * preparation of chunk k+1 runs in the SM slots the tail of chunk k's integration leaves idle.  Frame order =
+ * preparation order.  The buffers handed to prepare must stay valid until the matching integration is done.
+ */
+BSLAM_API int bslam_tsdf_prepare_u16(bslam_volume *vol, const uint16_t *d_depth_u16, float depth_scale, float depth_trunc,
+                                     float *d_depth_scratch, int F, int H, int W, const double *h_K, const double *h_extrinsics,
+                                     bslam_stream_t prep_stream);
+BSLAM_API int bslam_tsdf_integrate_prepared(bslam_volume *vol, const uint8_t *d_rgb, unsigned long long *d_update_counts,
+                                            bslam_stream_t stream);
+
 /* Round-robin z-sharding: this box holds every `stride_bricks`-th 8-voxel brick layer of the
  * grid, starting at global plane gz0 (= 8 * rank): local plane z is global plane
  * gz0 + (z / 8) * 8 * stride_bricks + z % 8.  Balances integration across ranks whatever the
