@@ -664,6 +664,22 @@ def main():
             log(f"SLAM cadence: {cadence['value']:.1f} frames/s ({cadence['ms_per_frame']:.2f} ms per integrate + extract_pcd)")
             del tsdf, frames
 
+        # ---- row f4: the tensor-pipeline integrator behind `MAP` (N/3DM/tsdf.py:56-108), reference defaults
+        # (voxel_size 5.8 mm, 16^3 blocks, trunc_voxel_multiplier 8) on a 256^3 box around the scene
+        try:
+            from bodyslam_b200.tsdf import MAP
+
+            Kmat = np.array([[cfg["K"][0], 0, cfg["K"][2]], [0, cfg["K"][1], cfg["K"][3]], [0, 0, 1.0]])
+            mp = MAP(W, H, Kmat, "CUDA:0" if dev.index == 0 else f"CUDA:{dev.index}", 1000.0, resolution=256, color=False)
+            n_map = min(F, 256)
+            poses = np.stack([np.linalg.inv(E[i]) for i in range(n_map)])
+            ms = timed(lambda: mp.integrate_batch(depth_u16[:n_map], None, poses, 3.0), n=3, warm=1)
+            extras["map_tensor_pipeline"] = {"frames_per_s": n_map / (ms / 1e3), "frames": n_map, "voxel_size_m": 0.0058, "resolution": 256,
+                                             "mesh_triangles": int(mp.extract_mesh().triangles.shape[0]), "clip": mp.clip_stats()}
+            del mp
+        except Exception as e:      # the extra leg must never take the headline down
+            extras["map_tensor_pipeline"] = {"error": f"{type(e).__name__}: {e}"}
+
         # ---- BASELINE configs[2]: 64-frame batched 1080p depth scale + colorize + back-project
         from bodyslam_b200 import mdem
 
