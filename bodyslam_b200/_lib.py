@@ -19,6 +19,7 @@ _SIGNATURES = {
     "bslam_last_error": (C.c_char_p, []),
     "bslam_version": (C.c_int, []),
     "bslam_device_count": (C.c_int, []),
+    "bslam_invert4x4": (C.c_int, [_p, _p, C.c_int]),
     "bslam_scale_u16": (C.c_int, [_p, C.c_int64, C.c_float, _p, _p]),
     "bslam_colorize_workspace_bytes": (C.c_size_t, [C.c_int]),
     "bslam_colorize": (C.c_int, [_p, _p, C.c_int, C.c_int, C.c_int, C.c_float, _p, _p, _p, C.c_double, C.c_double,

@@ -21,22 +21,14 @@ def to_numpy(x):
 def inverse4x4(m):
     """General 4x4 inverse by cofactors, row-major float64 -- the formula Eigen's `Matrix4d::inverse()` evaluates
     (Open3D: `extrinsic.inverse()` in CreateFromDepthImage / ScalableTSDFVolume::Integrate), so that the camera
-    pose handed to the kernels has Open3D's rounding rather than LAPACK's.  Accepts [..., 4, 4]."""
-    a = np.asarray(m, dtype=np.float64)
-    flat = a.reshape(-1, 4, 4)
-    out = np.empty_like(flat)
-    for n, M in enumerate(flat):
-        c = np.empty((4, 4))
-        for i in range(4):
-            for j in range(4):
-                minor = np.delete(np.delete(M, j, axis=0), i, axis=1)
-                d3 = (minor[0, 0] * (minor[1, 1] * minor[2, 2] - minor[1, 2] * minor[2, 1])
-                      - minor[0, 1] * (minor[1, 0] * minor[2, 2] - minor[1, 2] * minor[2, 0])
-                      + minor[0, 2] * (minor[1, 0] * minor[2, 1] - minor[1, 1] * minor[2, 0]))
-                c[i, j] = -d3 if (i + j) & 1 else d3
-        det = M[0, 0] * c[0, 0] + M[0, 1] * c[1, 0] + M[0, 2] * c[2, 0] + M[0, 3] * c[3, 0]
-        out[n] = c / det
-    return out.reshape(a.shape)
+    pose handed to the kernels has Open3D's rounding rather than LAPACK's.  Accepts [..., 4, 4]; evaluated by the
+    library's host helper (bslam_invert4x4), the same routine the unit-activation kernel's poses come from."""
+    from . import _lib
+
+    a = np.ascontiguousarray(m, dtype=np.float64)
+    out = np.empty_like(a)
+    _lib.check(_lib.load().bslam_invert4x4(_lib.ptr(a), _lib.ptr(out), a.size // 16))
+    return out
 
 
 class PinholeCameraIntrinsic:

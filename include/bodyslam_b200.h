@@ -124,6 +124,11 @@ BSLAM_API int bslam_median_u16(const uint16_t *d_u16, int B, int64_t n_per_image
 BSLAM_API int bslam_depth_from_u16(const uint16_t *d_in, int64_t n, float depth_scale,
                                    float depth_trunc, float *d_out, bslam_stream_t stream);
 
+/* Host helper: n row-major 4x4 float64 matrices inverted by the cofactor (adjugate / determinant) formula, the one
+ * Eigen's Matrix4d::inverse() evaluates for Open3D's `extrinsic.inverse()` -- the camera pose of back-projection and
+ * unit activation.  No device work. */
+BSLAM_API int bslam_invert4x4(const double *h_in, double *h_out, int n);
+
 /* ------------------------------------------------------------------ back-projection (K2)
  * Replaces `pixel_to_3d` N/3DM/scaling_system.py:72-77 applied densely, i.e. Open3D
  * PointCloud.create_from_depth_image / create_from_rgbd_image(depth, intrinsic, extrinsic)
