@@ -60,6 +60,7 @@ def parse():
     ap.add_argument("--settle", type=float, default=1.5, help="seconds of untimed steps before the warm-up (device clocks / memory settle)")
     ap.add_argument("--cpu-budget", type=float, default=6.0, help="seconds of CPU oracle work per timed CPU leg")
     ap.add_argument("--deviation", action="store_true", help="also quantify brick-restart vs literal z recurrence over all frames (slow validation kernel)")
+    ap.add_argument("--zpw", type=int, default=0, help="z layers per integrate warp (0 = library default; tuning aid)")
     ap.add_argument("--const-depth", type=int, default=0, help="EXPERIMENT: replace every frame by this constant uint16 depth (limit studies with BSLAM_EXPERIMENT; not a bench value)")
     ap.add_argument("--resident-layout", default="rank0", choices=["rank0", "sharded"],
                     help="N > 1, where the resident u16 frames live before the timed region: all on rank 0 (NCCL broadcast per chunk) or 1/N of every "
@@ -367,6 +368,8 @@ def main():
         interleaved = sh.layout == "interleaved"
     if args.batch:
         vol.set_batch(args.batch)
+    if args.zpw:
+        vol.set_z_split(args.zpw)
     chunk = args.batch or 256
     chunks = vol.stream_chunks(F, chunk, ramp=ShardedTSDF.stream_ramp(world, True))   # integrate launches of a resident step
 
