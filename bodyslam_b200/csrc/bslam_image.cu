@@ -30,8 +30,8 @@ __device__ __forceinline__ ImgStats *ws_stats(void *ws, int b) { return (ImgStat
 
 __device__ __forceinline__ unsigned int to_u16_sat(float m, float scale_mul) {
     // numpy: (metres * 256).astype(uint16) -- f32 multiply, truncation toward zero.
-    const float s = m * scale_mul;
-    return (unsigned int)fminf(fmaxf(truncf(s), 0.0f), 65535.0f); // NaN -> 0
+    // one saturating conversion (round toward zero; negative and NaN -> 0) and an integer clamp
+    return min(__float2uint_rz(m * scale_mul), 65535u);
 }
 
 // ---------------------------------------------------------------- K1 pass A: scale + histogram
