@@ -142,5 +142,8 @@ def update_map_after_pg(global_extrinsic, list_of_rgb, list_of_depth, depth_scal
     dev = tsdf.tsdf.device
     depth_u16, rgb = load_frames(list_of_rgb, list_of_depth, n, depth_scale, 3.0, dev)
     E = np.stack([np.asarray(to_numpy(e), dtype=np.float64) for e in global_extrinsic])
+    if "origin" not in tsdf_kwargs:     # no box given: centre it on what the first frame sees (TSDF.auto_centre)
+        tsdf.auto_centre(ops.depth_from_u16(depth_u16[0], depth_scale, 3.0, dev), intrinsic, E[0])
+        dev = tsdf.tsdf.device
     tsdf.tsdf.integrate_host(depth_u16, rgb if tsdf.tsdf.color else None, intrinsic, E, depth_scale=depth_scale, depth_trunc=3.0)
     return tsdf

@@ -534,17 +534,62 @@ class TSDF:
         8, tsdf.py:11-12): a frame only integrates the 32^3 units its sampled depth points activate, exactly
         what the reference object does; False = every voxel of the box follows the UniformTSDFVolume rule
         (the dense form BASELINE.json's north_star asks for).  None (default): True when the box consists
-        of whole units on the world unit grid (the default 512^3 box does), else False."""
+        of whole units on the world unit grid (the default 512^3 box does), else False.
+
+        origin: world position of the box corner.  None (default): the box starts centred on the world origin and
+        is RE-CENTRED ON THE FIRST FRAME's back-projected depth points (snapped to the 32-voxel unit grid) when that
+        frame would otherwise mostly fall outside it -- the reference's hashed volume is unbounded, and its SLAM
+        loop starts at the identity pose looking down +z (N/3DM/slam.py), i.e. at a surface that lies in front of,
+        not around, the origin."""
         res = (int(resolution),) * 3 if np.isscalar(resolution) else tuple(int(r) for r in resolution)
         org = origin if origin is not None else tuple(-0.5 * r * voxel_length for r in res)
+        self._auto_origin = origin is None
+        self._unit_request = unit_activation
+        self._make = lambda o, ua: DenseTSDFVolume(voxel_length=voxel_length, sdf_trunc=sdf_trunc, resolution=resolution, origin=o,
+                                                   color=color, device=device, unit_activation=ua)
         if unit_activation is None:
             unit_activation = DenseTSDFVolume.unit_aligned(res, voxel_length, org)
-        self.tsdf = DenseTSDFVolume(voxel_length=voxel_length, sdf_trunc=sdf_trunc, resolution=resolution, origin=origin,
-                                    color=color, device=device, unit_activation=bool(unit_activation))
+        self.tsdf = self._make(origin, bool(unit_activation))
         if not unit_activation:
             self.tsdf.set_clip_check(8)
         self._clip_warned = 0.0
         self._next_clip_check = 1      # frames_integrated at which the next (synchronising) clip check is due
+
+    def auto_centre(self, depth, intrinsic, extrinsic) -> bool:
+        """Called with the first frame (f32 metres, H x W) when no origin was given: if fewer than half of its
+        stride-8 back-projected points fall inside the (still empty) box, rebuild the box centred on their median,
+        snapped to the 32-voxel unit grid.  Returns True when the box moved."""
+        import warnings
+
+        if not self._auto_origin or self.tsdf.frames_integrated:
+            return False
+        self._auto_origin = False
+        torch = _lib.require_cuda()
+        v = self.tsdf
+        W, H, fx, fy, cx, cy = intrinsic_params(intrinsic)
+        d = ops.as_cuda(depth, torch.float32, v.device).reshape(1, H, W)
+        xyz, _ = ops.backproject(d, (fx, fy, cx, cy), np.asarray(to_numpy(extrinsic), dtype=np.float64).reshape(1, 4, 4), stride=8, device=v.device)
+        if xyz.shape[0] == 0:
+            return False
+        ext = np.array([v.nx, v.ny, v.nz]) * v.voxel_length
+        lo = torch.as_tensor(v.origin, dtype=torch.float32, device=v.device)
+        hi = torch.as_tensor(v.origin + ext, dtype=torch.float32, device=v.device)
+        inside = float(((xyz >= lo) & (xyz < hi)).all(dim=1).float().mean().item())
+        if inside >= 0.5:
+            return False
+        centre = xyz.median(dim=0).values.cpu().numpy().astype(np.float64)
+        ul = v.voxel_length * 32
+        new_origin = np.floor((centre - 0.5 * ext) / ul + 0.5) * ul
+        ua = self._unit_request
+        if ua is None:
+            ua = DenseTSDFVolume.unit_aligned((v.nx, v.ny, v.nz), v.voxel_length, new_origin)
+        self.tsdf = self._make(tuple(new_origin), bool(ua))
+        if not ua:
+            self.tsdf.set_clip_check(8)
+        warnings.warn(f"TSDF: only {100 * inside:.0f} % of the first frame's depth points fell inside the default box around the world "
+                      f"origin; the box was re-centred on them: origin = ({new_origin[0]:.3f}, {new_origin[1]:.3f}, {new_origin[2]:.3f}) m, "
+                      f"edge {ext[0]:.3f} m (pass origin= / resolution= to TSDF() to choose the box yourself)")
+        return True
 
     def clipped_fraction(self) -> float:
         """share of the sampled depth points integrated so far that fell OUTSIDE the bounded box (the
@@ -578,9 +623,13 @@ class TSDF:
         :param extrinsic: the global position of the camera
         :return:
         '''
+        if self._auto_origin and ops._dtype_name(rgbd.depth) == "float32":
+            self.auto_centre(rgbd.depth, intrinsic, extrinsic)
         self.tsdf.integrate(rgbd, intrinsic, extrinsic)
 
     def build_copy_3D_map(self, rgbd, intrinsic, extrinsic):
+        if self._auto_origin and ops._dtype_name(rgbd.depth) == "float32":
+            self.auto_centre(rgbd.depth, intrinsic, extrinsic)
         tsdf_copy = _copy.deepcopy(self.tsdf)
         tsdf_copy.integrate(rgbd, intrinsic, extrinsic)
         return tsdf_copy

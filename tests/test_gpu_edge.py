@@ -112,3 +112,32 @@ def test_drop_in_tsdf_rejects_mismatched_frames_like_open3d(cuda):
         t.build_3D_map(RGBDImage(None, d), sc["intrinsic"], sc["E"][0])                                          # RGB8 volume without colour
     with pytest.raises(RuntimeError, match="Unsupported image format"):
         t.build_3D_map(RGBDImage(sc["color"][0], sc["depth_u16"][0]), sc["intrinsic"], sc["E"][0])               # u16 depth: Open3D wants float
+
+
+def test_default_box_recentres_on_the_first_frame(cuda):
+    """`TSDF()` with no origin: the reference's SLAM loop starts at the identity pose looking at a surface 0.3 - 0.5 m
+    ahead (depth PNG / 1000), which lies outside a box centred on the world origin -- the box follows the first frame
+    (with a warning); an explicit origin is left alone"""
+    from bodyslam_b200.geometry import RGBDImage
+    K = (383.19, 383.19, 276.47, 124.33)             # the reference's 600x480 intrinsics (N/3DM/slam.py:25)
+    intr = PinholeCameraIntrinsic(600, 480, *K)
+    yy, xx = np.mgrid[0:480, 0:600]
+    depth = (0.40 + 0.05 * np.sin(xx / 60.0) * np.cos(yy / 45.0)).astype(np.float32)
+    color = np.full((480, 600, 3), 120, np.uint8)
+    t = TSDF(device=cuda)                            # the reference's constructor call: TSDF()
+    assert np.allclose(t.tsdf.origin, -0.256)
+    with pytest.warns(UserWarning, match="re-centred"):
+        t.build_3D_map(RGBDImage(color, depth), intr, np.eye(4))
+    assert t.tsdf.unit_activation and abs(t.tsdf.origin[2] + 0.256 - 0.40) < 0.05
+    st = t.tsdf.clip_stats()
+    assert st["outside"] < 0.35 * st["points"]       # the 0.512 m box holds the central part of the 0.6 m wide view
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        assert t.extract_mesh().triangles.shape[0] > 10000
+    # an explicit origin is respected (and the clip warning tells the user what was lost)
+    t2 = TSDF(origin=(-0.256,) * 3, device=cuda)
+    t2.build_3D_map(RGBDImage(color, depth), intr, np.eye(4))
+    assert np.allclose(t2.tsdf.origin, -0.256)
+    with pytest.warns(UserWarning, match="outside the volume box"):
+        t2.extract_pcd()
