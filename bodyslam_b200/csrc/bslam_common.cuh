@@ -134,6 +134,8 @@ struct bslam_volume {
     cudaEvent_t slot_ready[2], slot_free[2];
     int slot_used[2], slot_prof[2], slot_tiles[2][2];
     int prep_head, prep_tail, prep_pending;
+    cudaStream_t hp_stream;                   // private high-priority stream of the pipelined integration
+    cudaEvent_t hp_fence;
     int clip_stride;                          // dense mode: sampling stride of the out-of-box point count (0 = off)
     int z_total;                              // planes of the whole grid when this box is a z-shard (clip check)
     static constexpr int kProfPairs = 1024;   // integrate launches timed per bslam_tsdf_profile_read

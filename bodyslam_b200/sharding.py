@@ -363,7 +363,9 @@ class ShardedTSDF:
                     # stream that is current at the call); NCCL has no 16-bit integer type: ship bytes
                     return dist.broadcast(u16.view(torch.uint8), src, group=self.group, async_op=True)
 
-            vol.prep_stream().wait_stream(main)
+            pipelined = vol.pipeline_enabled()
+            if pipelined:
+                vol.prep_stream().wait_stream(main)
 
             def prep(k):     # conversion + statistics + culling of chunk k on the side stream, once its frames have arrived
                 f0, f1 = chunks[k]
@@ -372,13 +374,19 @@ class ShardedTSDF:
             works = {0: issue(0)}
             if len(chunks) > 1:
                 works[1] = issue(1)
-            prep(0)
+            if pipelined:
+                prep(0)
             for k, (f0, f1) in enumerate(chunks):
                 if k + 2 < len(chunks):
                     works[k + 2] = issue(k + 2)
-                if k + 1 < len(chunks):
-                    prep(k + 1)                                    # overlaps the integration of chunk k
-                vol.integrate_prepared(None, None if update_counts is None else update_counts[f0:f1])
+                cnt = None if update_counts is None else update_counts[f0:f1]
+                if pipelined:
+                    if k + 1 < len(chunks):
+                        prep(k + 1)                                # overlaps the integration of chunk k
+                    vol.integrate_prepared(None, cnt)
+                else:
+                    works.pop(k).wait()                            # current stream waits for chunk k
+                    vol.integrate_u16_batch(bufs.pop(k), None, intrinsic, E[f0:f1], depth_scale, depth_trunc, scratch=stage[k % 3][1], update_counts=cnt)
                 free[k % 3] = torch.cuda.Event()
                 free[k % 3].record(main)
 
@@ -460,7 +468,9 @@ class ShardedTSDF:
                                 works.append(dist.broadcast(u8[q0 - f0:q1 - f0], q, group=self.group, async_op=True))
                 return works
 
-            vol.prep_stream().wait_stream(main)
+            pipelined = vol.pipeline_enabled()
+            if pipelined:
+                vol.prep_stream().wait_stream(main)
 
             def prep(k):
                 f0, f1 = chunks[k]
@@ -471,13 +481,21 @@ class ShardedTSDF:
             pending = {0: issue(0)}
             if len(chunks) > 1:
                 pending[1] = issue(1)
-            prep(0)
+            if pipelined:
+                prep(0)
             for k, (f0, f1) in enumerate(chunks):
                 if k + 2 < len(chunks):
                     pending[k + 2] = issue(k + 2)
-                if k + 1 < len(chunks):
-                    prep(k + 1)                                      # overlaps the integration of chunk k
-                vol.integrate_prepared(None, None if update_counts is None else update_counts[f0:f1])
+                cnt = None if update_counts is None else update_counts[f0:f1]
+                if pipelined:
+                    if k + 1 < len(chunks):
+                        prep(k + 1)                                  # overlaps the integration of chunk k
+                    vol.integrate_prepared(None, cnt)
+                else:
+                    for w in pending.pop(k):
+                        w.wait()                                     # current stream waits for chunk k
+                    vol.integrate_u16_batch(stage[k % 3][0][:f1 - f0], None, intrinsic, E[f0:f1], depth_scale, depth_trunc,
+                                            scratch=stage[k % 3][1], update_counts=cnt)
                 free[k % 3] = torch.cuda.Event()
                 free[k % 3].record(main)
 

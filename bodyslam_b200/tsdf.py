@@ -201,6 +201,12 @@ class DenseTSDFVolume:
         return scratch
 
     # ------------------------------------------------------------------ two-stream launch pipeline
+    @staticmethod
+    def pipeline_enabled() -> bool:
+        """BODYSLAM_PIPELINE=0 makes the streamed entry points run preparation and integration back to back on one
+        stream (measurement switch; the default overlaps the preparation of chunk k+1 with the integration of chunk k)"""
+        return os.environ.get("BODYSLAM_PIPELINE", "1") != "0"
+
     def prep_stream(self):
         """side stream for the part of a launch that does not touch the volume (conversion, statistics, culling)"""
         torch = _lib.require_cuda()
@@ -253,6 +259,11 @@ class DenseTSDFVolume:
         torch = _lib.require_cuda()
         E = np.asarray(to_numpy(extrinsics), dtype=np.float64).reshape(-1, 4, 4)
         if not chunks:
+            return
+        if not self.pipeline_enabled():
+            for f0, f1 in chunks:
+                self.integrate_u16_batch(depth_u16[f0:f1], None if color is None else color[f0:f1], intrinsic, E[f0:f1], depth_scale, depth_trunc,
+                                         update_counts=None if update_counts is None else update_counts[f0:f1])
             return
         H, W = depth_u16.shape[1], depth_u16.shape[2]
         stage = self._staging(max(f1 - f0 for f0, f1 in chunks), H, W, False, count=3)
