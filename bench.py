@@ -348,7 +348,7 @@ def main():
     lo, hi = min(rank * per, F), min((rank + 1) * per, F)
     depth_u16 = torch.zeros((per * world, H, W), dtype=torch.uint16, device=dev)
     if hi > lo:
-        depth_u16[lo:hi] = S.render(cfg["surface"], E[lo:hi], K=cfg["K"], W=W, H=H, device=dev, with_color=False)[0]
+        depth_u16[lo:hi] = S.render(cfg["surface"], E[lo:hi], K=cfg["K"], W=W, H=H, device=dev, with_color=False, first_frame=lo)[0]
     if world > 1:
         dist.all_gather_into_tensor(depth_u16.view(torch.uint8), depth_u16[rank * per:(rank + 1) * per].view(torch.uint8).clone())
     depth_u16 = depth_u16[:F]
@@ -667,6 +667,16 @@ def main():
             log(f"SLAM cadence: {cadence['value']:.1f} frames/s ({cadence['ms_per_frame']:.2f} ms per integrate + extract_pcd)")
             del tsdf, frames
 
+        # ---- dense rule with the reference's per-unit arithmetic (literal Open3D voxel centres + z recurrence per 32^3 unit)
+        if res % 32 == 0:
+            uvol = DenseTSDFVolume(vl, trunc, res, unit_origin(cfg["origin"], vl), color=False, device=dev, unit_arithmetic=True)
+            uchunks = DenseTSDFVolume.stream_chunks(F, chunk, ramp=())
+            ms = timed(lambda: uvol.integrate_u16_chunks(depth_u16, None, intr, E, uchunks, 1000.0, 3.0), n=max(3, args.steps // 4))
+            extras["dense_unit_arithmetic"] = {"value": F / (ms / 1e3), "unit": UNIT, "ms_per_step": ms,
+                                               "what": "every voxel of the box integrated (dense rule) with ScalableTSDFVolume's per-unit voxel centres and float32 z "
+                                                       "recurrence: the oracle runs Open3D's literal arithmetic (z_restart 0), nothing bent to the kernel"}
+            del uvol
+
         # ---- row f4: the tensor-pipeline integrator behind `MAP` (N/3DM/tsdf.py:56-108), reference defaults
         # (voxel_size 5.8 mm, 16^3 blocks, trunc_voxel_multiplier 8) on a 256^3 box around the scene
         try:
@@ -745,7 +755,8 @@ def main():
         sel = torch.as_tensor(ids, device=dev)
         sample_u16 = depth_u16.view(torch.int16)[sel].view(torch.uint16)
         _, sample_rgb = S.render(cfg["surface"], E[ids], K=cfg["K"], W=W, H=H, device=dev, with_color=True)
-        legs = cpu_legs(cfg, E, sample_u16.cpu().numpy(), sample_rgb.cpu().numpy(), ids, res, vl, trunc, args.cpu_budget)
+        su16_np = sample_u16.cpu().numpy()
+        legs = cpu_legs(cfg, E, su16_np, sample_rgb.cpu().numpy(), ids, res, vl, trunc, args.cpu_budget)
         log(f"CPU oracle: dense {legs['dense_fps']:.1f} frames/s ({legs['dense_frames']} frames), scalable {legs.get('scalable_fps', 0):.1f}, "
             f"scalable with Open3D's schedule {legs.get('scalable_open3d_schedule_fps', 0):.1f}, {legs['cores']} threads")
         # dense rule
@@ -784,6 +795,19 @@ def main():
                                        "mesh_vertices": int(gm.vertices.shape[0]), "mesh_triangles": int(gm.triangles.shape[0]), "occupied_voxels": int(Sv.occupied()),
                                        "oracle": "oracle/o3d_oracle.c orc_scalable_integrate (z_restart 0 = Open3D's literal per-unit recurrence) + orc_extract_mesh"}
             del Sv, g, t, w, c, gm, om
+        if res % 32 == 0:
+            n = min(legs["dense_frames"], 48)
+            org_u = unit_origin(cfg["origin"], vl)
+            Av = oracle.o3d.Volume(res, vl, trunc, org_u)
+            ac = [int(Av.integrate_scalable(oracle.o3d.depth_from_u16(su16_np[k]), cfg["K"], E[ids[k]], all_units=True)) for k in range(n)]
+            g = DenseTSDFVolume(vl, trunc, res, org_u, color=False, device=dev, unit_arithmetic=True)
+            gc = torch.zeros(n, dtype=torch.int64, device=dev)
+            g.integrate_u16_batch(sample_u16[:n], None, intr, E[ids[:n]], 1000.0, 3.0, update_counts=gc)
+            t, w = g.export_dense()
+            parity["dense_unit_arithmetic"] = {"frames": n, "resolution": res, "tsdf_equal": digest(t.cpu().numpy()) == digest(Av.tsdf),
+                                               "weight_equal": digest(w.cpu().numpy()) == digest(Av.weight), "update_counts_equal": gc.cpu().tolist() == ac,
+                                               "oracle": "oracle/o3d_oracle.c orc_scalable_integrate, every unit touched, z_restart 0 (Open3D's literal per-unit arithmetic)"}
+            del Av, g, t, w
         if cadence is not None:
             # the same cadence on the CPU oracle (ScalableTSDFVolume rule + extract_point_cloud), first frames of the trajectory
             n_c = 3

@@ -76,6 +76,7 @@ struct VolView {
     // ScalableTSDFVolume mode (0 = off): the box consists of whole units of unit_res^3 voxels on the
     // world unit grid, origin = u0 * unit_len; only units activated by a frame are integrated by it
     int unit_res, unit_shift, unit_stride;   // unit_res = 1 << unit_shift
+    int unit_nomask;     // 1: per-unit ARITHMETIC (voxel centres, z recurrence) for every unit of the box, no activation mask
     int u0[3];
     int nux, nuy, nuz;   // units per axis (z: of the whole grid when the box is a z-shard)
     double unit_len;

@@ -149,8 +149,10 @@ def _dropout_mask(shape, seed, frac, device):
 
 
 def render(surface, extrinsics, K=K_640, W=640, H=480, device="cpu", invalid_frac=0.02, depth_scale=1000.0,
-           with_color=True, seed=0, chunk=16):
-    """-> depth_u16 [F,H,W] (3DM units: metres * depth_scale, 0 = invalid), color u8 [F,H,W,3] | None."""
+           with_color=True, seed=0, chunk=16, first_frame=0):
+    """-> depth_u16 [F,H,W] (3DM units: metres * depth_scale, 0 = invalid), color u8 [F,H,W,3] | None.
+    first_frame: trajectory index of extrinsics[0] -- the invalid-pixel pattern of a frame depends on its index in the
+    trajectory, so a trajectory rendered in pieces (one piece per rank) equals the one rendered in one go."""
     device = torch.device(device)
     E = np.asarray(extrinsics, dtype=np.float64).reshape(-1, 4, 4)
     F = E.shape[0]
@@ -162,7 +164,7 @@ def render(surface, extrinsics, K=K_640, W=640, H=480, device="cpu", invalid_fra
         t = surface.depth(o, d)
         q = torch.floor(t * depth_scale + 0.5).clamp(0, 65535)
         if invalid_frac > 0:
-            q = torch.where(_dropout_mask((H, W), seed * 100003 + f, invalid_frac, device), torch.zeros_like(q), q)
+            q = torch.where(_dropout_mask((H, W), seed * 100003 + first_frame + f, invalid_frac, device), torch.zeros_like(q), q)
         depth[f] = q.to(torch.int32).to(torch.uint16)
         if with_color:
             p = o + t[..., None] * d

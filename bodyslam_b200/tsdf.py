@@ -32,7 +32,7 @@ class DenseTSDFVolume:
 
     def __init__(self, voxel_length: float, sdf_trunc: float, resolution=512, origin=None, color: bool = True,
                  device=None, gz0: int = 0, z_total: int | None = None, z_interleave: int = 1,
-                 unit_activation: bool = False, unit_resolution: int = 32, depth_sampling_stride: int = 8):
+                 unit_activation: bool = False, unit_resolution: int = 32, depth_sampling_stride: int = 8, unit_arithmetic: bool = False):
         torch = _lib.require_cuda()
         self._L = _lib.load()
         self.device = ops._device(device)
@@ -58,8 +58,15 @@ class DenseTSDFVolume:
         if self.z_interleave != 1:
             _lib.check(self._L.bslam_tsdf_set_z_interleave(self._h, self.z_interleave))
         self.unit_activation = bool(unit_activation)
+        self.unit_arithmetic = bool(unit_arithmetic) and not self.unit_activation
         if self.unit_activation:
             self.set_unit_activation(unit_resolution, depth_sampling_stride)
+        elif self.unit_arithmetic:
+            # dense rule (every voxel of the box) with the reference's per-unit arithmetic: voxel centres and the float32 z
+            # recurrence evaluated per 32^3 unit like ScalableTSDFVolume's units -- on the voxels of the units the reference
+            # would have activated the result is the reference's, bit for bit (oracle: integrate_scalable(all_units=True))
+            _lib.check(self._L.bslam_tsdf_set_unit_activation(self._h, int(unit_resolution), -1, int(self.z_total)))
+            self.unit_resolution, self.depth_sampling_stride = int(unit_resolution), -1
         self.frames_integrated = 0
 
     def set_unit_activation(self, unit_resolution: int = 32, depth_sampling_stride: int = 8):
@@ -107,7 +114,8 @@ class DenseTSDFVolume:
         torch = _lib.require_cuda()
         other = DenseTSDFVolume(self.voxel_length, self.sdf_trunc, (self.nx, self.ny, self.nz), self.origin, self.color,
                                 self.device, self.gz0, self.z_total, self.z_interleave, self.unit_activation,
-                                getattr(self, "unit_resolution", 32), getattr(self, "depth_sampling_stride", 8))
+                                getattr(self, "unit_resolution", 32), max(getattr(self, "depth_sampling_stride", 8), 1),
+                                unit_arithmetic=self.unit_arithmetic)
         with torch.cuda.device(self.device):
             _lib.check(self._L.bslam_tsdf_copy(self._h, other._h, _lib.stream_ptr(self.device)))
         other.frames_integrated = self.frames_integrated

@@ -232,6 +232,9 @@ BSLAM_API int bslam_tsdf_set_batch(bslam_volume *vol, int frames_per_launch);
  * must consist of whole units on the world unit grid (origin = k * unit_resolution * voxel_length);
  * z_total: plane count of the whole grid when this volume is a z-shard (0 = nz).  0 switches back
  * to the dense UniformTSDFVolume semantics (default).
+ * depth_sampling_stride = -1: "dense with the reference's arithmetic" -- EVERY unit of the box is integrated by every
+ * frame (no activation mask), with the per-unit voxel centres and the per-unit float32 z recurrence; on the voxels of
+ * the units ScalableTSDFVolume would have activated the result equals the reference's bit for bit.
  */
 BSLAM_API int bslam_tsdf_set_unit_activation(bslam_volume *vol, int unit_resolution, int depth_sampling_stride, int z_total);
 

@@ -35,6 +35,7 @@ def lib():
                                          p, p, p, C.c_int, C.c_int, p, p, C.c_int]
         L.orc_invert4x4.argtypes = [p, p]
         L.orc_set_scalable_schedule.argtypes = [C.c_int]
+        L.orc_set_scalable_all_units.argtypes = [C.c_int]
         L.orc_scalable_integrate.restype = C.c_int64
         L.orc_scalable_integrate.argtypes = [p, p, p, C.c_int, C.c_int, C.c_int, p, C.c_int, C.c_int, C.c_double, C.c_double,
                                              p, p, C.c_int, C.c_int, p, p, p, C.c_int, p]
@@ -134,7 +135,7 @@ class Volume:
                                         self.nx, self.ny, self.nz, self.gz0, self.voxel_length, self.sdf_trunc,
                                         _ptr(self.origin), _ptr(d), _ptr(c), W, H, _ptr(Kd), _ptr(E), int(z_restart))
 
-    def integrate_scalable(self, depth_f32, K, extrinsic, rgb=None, z_restart=0, unit_res=32, stride=8, return_touched=False):
+    def integrate_scalable(self, depth_f32, K, extrinsic, rgb=None, z_restart=0, unit_res=32, stride=8, return_touched=False, all_units=False):
         """ScalableTSDFVolume.integrate (A.3 step 7; what `TSDF()` of N/3DM/tsdf.py:7-12 builds) on this dense
         box, which must consist of whole units aligned to the world unit grid (origin = k * unit_length).
         z_restart = 0 (default): Open3D's literal float32 recurrence inside every unit, from the unit's z = 0."""
@@ -152,6 +153,7 @@ class Volume:
             raise ValueError("scalable mode needs a box of whole units on the world unit grid")
         u0 = np.ascontiguousarray(u0, dtype=np.int32)
         touched = np.zeros((self.nx // unit_res) * (self.ny // unit_res) * (self.nz // unit_res), np.uint8)
+        lib().orc_set_scalable_all_units(1 if all_units else 0)      # all_units: every unit, no activation test (per-unit arithmetic only)
         n = lib().orc_scalable_integrate(_ptr(self.tsdf), _ptr(self.weight), _ptr(self.color if c is not None else None),
                                          self.nx, self.ny, self.nz, _ptr(u0), int(unit_res), int(stride), self.voxel_length,
                                          self.sdf_trunc, _ptr(d), _ptr(c), W, H, _ptr(Kd), _ptr(E), _ptr(M), int(z_restart), _ptr(touched))

@@ -224,6 +224,10 @@ ORC_API void orc_invert4x4(const double *a, double *out) {
  */
 static int g_scalable_schedule = 1;
 ORC_API void orc_set_scalable_schedule(int s) { g_scalable_schedule = s; }
+/* 1: every unit of the box is integrated by every frame (no activation test) -- the "dense box with the reference's
+ * per-unit arithmetic" mode of the product (bslam_tsdf_set_unit_activation with stride -1) */
+static int g_scalable_all_units = 0;
+ORC_API void orc_set_scalable_all_units(int a) { g_scalable_all_units = a; }
 
 ORC_API int64_t orc_scalable_integrate(float *tsdf, float *weight, float *color, int nx, int ny, int nz,
                                        const int *unit0, int unit_res, int stride, double voxel_length,
@@ -233,7 +237,9 @@ ORC_API int64_t orc_scalable_integrate(float *tsdf, float *weight, float *color,
     const int nux = nx / unit_res, nuy = ny / unit_res, nuz = nz / unit_res;
     const double unit_length = voxel_length * (double)unit_res;
     uint8_t *touched = (uint8_t *)calloc((size_t)nux * nuy * nuz, 1);
-    {
+    if (g_scalable_all_units) {
+        memset(touched, 1, (size_t)nux * nuy * nuz);
+    } else {
         const double fxd = K[0], fyd = K[1], cxd = K[2], cyd = K[3];
         const double *M = cam_to_world;
         for (int i = 0; i < H; i += stride)

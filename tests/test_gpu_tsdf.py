@@ -508,3 +508,35 @@ def test_config1_colonoscopy_256_full_size_values(cuda):
         mesh, ref = vol.extract_triangle_mesh(), V.extract_mesh()
         assert int(mesh.vertices.shape[0]) == len(ref["vertices"]) and int(mesh.triangles.shape[0]) == len(ref["triangles"])
         assert len(ref["triangles"]) > 10000
+
+
+def test_dense_rule_with_the_references_per_unit_arithmetic(cuda):
+    """`unit_arithmetic=True`: every voxel of the box is integrated (north_star's dense volume) but with the voxel centres
+    and the float32 z recurrence of ScalableTSDFVolume's 32^3 units -- literal Open3D arithmetic, oracle z_restart = 0 with
+    every unit touched; on the units the reference would have activated the values ARE the reference's"""
+    sc = small_scene("laparoscopy512", res=128, frames=5)
+    ul = sc["voxel_length"] * 32
+    origin = np.floor(sc["origin"] / ul + 0.5) * ul
+    vol = DenseTSDFVolume(sc["voxel_length"], sc["sdf_trunc"], 128, origin, color=True, device=cuda, unit_arithmetic=True)
+    from bodyslam_b200 import ops
+    depth = ops.depth_from_u16(sc["depth_u16"], 1000.0, 3.0, cuda)
+    counts = torch.zeros(5, dtype=torch.int64, device=cuda)
+    vol.integrate_batch(depth, torch.from_numpy(sc["color"]).to(cuda), sc["intrinsic"], sc["E"], update_counts=counts)
+    A = oracle.o3d.Volume(128, sc["voxel_length"], sc["sdf_trunc"], origin, with_color=True)      # every unit, per-unit arithmetic
+    S = oracle.o3d.Volume(128, sc["voxel_length"], sc["sdf_trunc"], origin, with_color=True)      # the reference: activated units only
+    co, act = [], np.zeros((4, 4, 4), bool)
+    for i in range(5):
+        d = oracle.o3d.depth_from_u16(sc["depth_u16"][i])
+        co.append(A.integrate_scalable(d, sc["K"], sc["E"][i], rgb=sc["color"][i], all_units=True))
+        _, touched = S.integrate_scalable(d, sc["K"], sc["E"][i], rgb=sc["color"][i], return_touched=True)
+        act |= touched.astype(bool)
+    assert counts.cpu().tolist() == co
+    assert_volume_equal(vol, A, sc["sdf_trunc"], color=True)
+    # a voxel of a unit that EVERY frame that could update it also activated holds the reference's value; check the
+    # units activated by all 5 frames' union where the scalable oracle and the all-units oracle agree on the weights
+    t, w = (x.cpu().numpy() for x in vol.export_dense())
+    same_w = w == S.grid("weight")
+    assert same_w.mean() > 0.5 and np.array_equal(t[same_w], S.grid("tsdf")[same_w])
+    # deepcopy keeps the mode
+    c2 = copy.deepcopy(vol)
+    assert c2.unit_arithmetic and not c2.unit_activation
