@@ -238,7 +238,7 @@ class ShardedTSDF:
     """
 
     def __init__(self, voxel_length=0.001, sdf_trunc=0.1, resolution=512, origin=None, color=True, device=None,
-                 rank=None, world_size=None, group=None, layout="interleaved", unit_activation=None):
+                 rank=None, world_size=None, group=None, layout="interleaved", unit_activation=None, unit_arithmetic=False):
         """unit_activation: like `TSDF` -- True = ScalableTSDFVolume semantics (a frame integrates only the 32^3
         units its sampled points activate), False = dense UniformTSDFVolume rule, None (default) = True when the
         whole grid consists of whole units on the world unit grid.  Same default as `TSDF`, so the sharded map
@@ -259,6 +259,8 @@ class ShardedTSDF:
         if unit_activation is None:
             unit_activation = DenseTSDFVolume.unit_aligned(resolution, voxel_length, origin)
         self.unit_activation = bool(unit_activation)
+        # dense rule with the reference's per-unit arithmetic (see DenseTSDFVolume); ignored in unit-activation mode
+        self.unit_arithmetic = bool(unit_arithmetic) and not self.unit_activation
         self._args = dict(voxel_length=voxel_length, sdf_trunc=sdf_trunc, origin=origin, color=color, device=device)
         n_layers = self.nz // BRICK
         if self.world_size == 1 or self.nz % BRICK or n_layers % self.world_size:
@@ -267,11 +269,11 @@ class ShardedTSDF:
         if layout == "interleaved":
             self.tsdf = DenseTSDFVolume(voxel_length, sdf_trunc, (self.nx, self.ny, self.nz // self.world_size), origin, color=color,
                                         device=device, gz0=BRICK * self.rank, z_total=self.nz, z_interleave=self.world_size,
-                                        unit_activation=self.unit_activation)
+                                        unit_activation=self.unit_activation, unit_arithmetic=self.unit_arithmetic)
         else:
             z0, z1 = self.bounds[self.rank]
             self.tsdf = DenseTSDFVolume(voxel_length, sdf_trunc, (self.nx, self.ny, z1 - z0), origin, color=color, device=device,
-                                        gz0=z0, z_total=self.nz, unit_activation=self.unit_activation)
+                                        gz0=z0, z_total=self.nz, unit_activation=self.unit_activation, unit_arithmetic=self.unit_arithmetic)
 
     def integrate_batch(self, depth, color, intrinsic, extrinsics, broadcast_from=None):
         if broadcast_from is not None and self.world_size > 1:
@@ -513,7 +515,8 @@ class ShardedTSDF:
         slab = getattr(self, "_slab", None)
         if slab is None:      # kept across calls: every brick layer (voxels, colour, flags) is overwritten by the re-shard
             slab = self._slab = DenseTSDFVolume(a["voxel_length"], a["sdf_trunc"], (self.nx, self.ny, z1 - z0), a["origin"], color=a["color"],
-                                                device=self.tsdf.device, gz0=z0, z_total=self.nz, unit_activation=self.unit_activation)
+                                                device=self.tsdf.device, gz0=z0, z_total=self.nz, unit_activation=self.unit_activation,
+                                                unit_arithmetic=self.unit_arithmetic)
         send, recv = reshard_plan(self.nz // BRICK, self.world_size, self.rank)
         src, dst = self.tsdf.storage_layers(), slab.storage_layers()
         for k in src:

@@ -24,7 +24,7 @@ def _worker(rank, world, port, ret, layout, unit=False):
         from bodyslam_b200.tsdf import DenseTSDFVolume
         from util import canon_mesh, small_scene
         sc = small_scene("laparoscopy512", res=128, frames=6, with_color=False)
-        sh = ShardedTSDF(sc["voxel_length"], sc["sdf_trunc"], 128, sc["origin"], color=False, device=dev, rank=rank, world_size=world, layout=layout, unit_activation=unit)
+        sh = ShardedTSDF(sc["voxel_length"], sc["sdf_trunc"], 128, sc["origin"], color=False, device=dev, rank=rank, world_size=world, layout=layout, unit_activation=(unit is True), unit_arithmetic=(unit == 'arith'))
         F, H, W = sc["depth_u16"].shape
         if rank == 0:
             depth = ops.depth_from_u16(sc["depth_u16"], 1000.0, 3.0, dev)
@@ -36,7 +36,7 @@ def _worker(rank, world, port, ret, layout, unit=False):
         mesh = sh.extract_mesh()
         # the streamed replay (pinned host u16 on rank 0 -> H2D -> NCCL broadcast -> fused a4 + integrate,
         # pipelined over chunks) must build the same shard, and report the same per-frame update counts
-        sh2 = ShardedTSDF(sc["voxel_length"], sc["sdf_trunc"], 128, sc["origin"], color=False, device=dev, rank=rank, world_size=world, layout=layout, unit_activation=unit)
+        sh2 = ShardedTSDF(sc["voxel_length"], sc["sdf_trunc"], 128, sc["origin"], color=False, device=dev, rank=rank, world_size=world, layout=layout, unit_activation=(unit is True), unit_arithmetic=(unit == 'arith'))
         counts = torch.zeros(F, dtype=torch.int64, device=dev)
         src = torch.from_numpy(sc["depth_u16"]).pin_memory() if rank == 0 else None
         sh2.integrate_stream(src if rank == 0 else torch.empty(0), sc["intrinsic"], sc["E"] if rank == 0 else np.zeros_like(sc["E"]), src=0, chunk=2,
@@ -44,19 +44,19 @@ def _worker(rank, world, port, ret, layout, unit=False):
         same = torch.equal(sh2.tsdf.export_dense()[0], sh.tsdf.export_dense()[0]) and torch.equal(sh2.tsdf.export_dense()[1], sh.tsdf.export_dense()[1])
         dist.all_reduce(counts)
         # sharded ingest: every rank feeds its share of each chunk from its own pinned host memory
-        sh3 = ShardedTSDF(sc["voxel_length"], sc["sdf_trunc"], 128, sc["origin"], color=False, device=dev, rank=rank, world_size=world, layout=layout, unit_activation=unit)
+        sh3 = ShardedTSDF(sc["voxel_length"], sc["sdf_trunc"], 128, sc["origin"], color=False, device=dev, rank=rank, world_size=world, layout=layout, unit_activation=(unit is True), unit_arithmetic=(unit == 'arith'))
         mine = ShardedTSDF.ingest_share(F, rank, world, 4)
         sh3.integrate_stream_sharded(torch.from_numpy(sc["depth_u16"][mine]).pin_memory(), sc["intrinsic"], sc["E"], chunk=4)
         same = same and torch.equal(sh3.tsdf.export_dense()[0], sh.tsdf.export_dense()[0]) and torch.equal(sh3.tsdf.export_dense()[1], sh.tsdf.export_dense()[1])
         # an odd frame count leaves a last chunk that does not divide evenly: per-piece broadcasts, device-resident shares
-        sh4 = ShardedTSDF(sc["voxel_length"], sc["sdf_trunc"], 128, sc["origin"], color=False, device=dev, rank=rank, world_size=world, layout=layout, unit_activation=unit)
+        sh4 = ShardedTSDF(sc["voxel_length"], sc["sdf_trunc"], 128, sc["origin"], color=False, device=dev, rank=rank, world_size=world, layout=layout, unit_activation=(unit is True), unit_arithmetic=(unit == 'arith'))
         mine = ShardedTSDF.ingest_share(5, rank, world, 4)
         sh4.integrate_stream_sharded(torch.from_numpy(sc["depth_u16"][mine]).to(dev), sc["intrinsic"], sc["E"][:5], chunk=4)
-        sh5 = ShardedTSDF(sc["voxel_length"], sc["sdf_trunc"], 128, sc["origin"], color=False, device=dev, rank=rank, world_size=world, layout=layout, unit_activation=unit)
+        sh5 = ShardedTSDF(sc["voxel_length"], sc["sdf_trunc"], 128, sc["origin"], color=False, device=dev, rank=rank, world_size=world, layout=layout, unit_activation=(unit is True), unit_arithmetic=(unit == 'arith'))
         sh5.integrate_batch(depth[:5].clone(), None, sc["intrinsic"], E[:5], broadcast_from=0)
         same = same and torch.equal(sh4.tsdf.export_dense()[0], sh5.tsdf.export_dense()[0]) and torch.equal(sh4.tsdf.export_dense()[1], sh5.tsdf.export_dense()[1])
         if rank == 0:
-            ref = DenseTSDFVolume(sc["voxel_length"], sc["sdf_trunc"], 128, sc["origin"], color=False, device=dev, unit_activation=unit)
+            ref = DenseTSDFVolume(sc["voxel_length"], sc["sdf_trunc"], 128, sc["origin"], color=False, device=dev, unit_activation=(unit is True), unit_arithmetic=(unit == 'arith'))
             ref.integrate_batch(depth, None, sc["intrinsic"], sc["E"])
             rm = ref.extract_triangle_mesh()
             a = canon_mesh(mesh.vertices.cpu().numpy(), mesh.vertex_keys.cpu().numpy(), mesh.triangles.cpu().numpy(), (128,) * 3)
@@ -78,10 +78,11 @@ def _worker(rank, world, port, ret, layout, unit=False):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("layout,unit", [("interleaved", False), ("contiguous", False), ("interleaved", True)])
+@pytest.mark.parametrize("layout,unit", [("interleaved", False), ("contiguous", False), ("interleaved", True), ("interleaved", "arith")])
 def test_sharded_mesh_equals_single_gpu_mesh(cuda, layout, unit):
     """unit=True: ScalableTSDFVolume unit activation on z-shards (the reference's TSDF() semantics, the default of
-    both TSDF and ShardedTSDF on unit-aligned boxes) -- the sharded map / mesh equals the single-GPU drop-in's"""
+    both TSDF and ShardedTSDF on unit-aligned boxes) -- the sharded map / mesh equals the single-GPU drop-in's;
+    unit="arith": dense rule with the reference's per-unit arithmetic on z-shards"""
     world = min(torch.cuda.device_count(), 4)
     if world < 2:
         pytest.skip("needs >= 2 GPUs")
