@@ -195,3 +195,46 @@ def test_sharded_ingest_ownership_partitions_every_chunk():
             assert all(np.all(np.diff(s) > 0) for s in shares if len(s) > 1)
     assert D.stream_chunks(1000, 256, multiple_of=8)[:3] == [(0, 32), (32, 96), (96, 224)]
     assert S.stream_ramp(1, True) == () and S.stream_ramp(8, True) == (64,) and S.stream_ramp(8, False) == (32, 64, 128)
+
+
+def test_inverse4x4_is_the_cofactor_formula_the_oracle_uses():
+    """camera poses handed to back-projection / unit activation: Eigen-style cofactor inverse (host helper of the C ABI)"""
+    import oracle
+    from bodyslam_b200.geometry import inverse4x4
+    rng = np.random.default_rng(0)
+    E = rng.normal(size=(16, 4, 4))
+    E[:, 3] = [0, 0, 0, 1]
+    inv = inverse4x4(E)
+    assert inv.shape == E.shape and np.abs(inv - np.linalg.inv(E)).max() < 1e-9
+    for k in range(16):
+        M = np.zeros(16)
+        oracle.o3d.lib().orc_invert4x4(np.ascontiguousarray(E[k]).ctypes.data, M.ctypes.data)
+        assert np.abs(M.reshape(4, 4) - inv[k]).max() <= 4 * np.finfo(np.float64).eps * np.abs(inv[k]).max()
+    assert np.array_equal(inverse4x4(np.eye(4)), np.eye(4))
+
+
+def test_map_and_tsdf_signatures_match_the_reference():
+    import inspect
+    from bodyslam_b200.tsdf import MAP, TSDF
+    p = inspect.signature(MAP.__init__).parameters
+    assert list(p)[1:9] == ["width", "height", "intrinsic", "device", "depth_scale", "voxel_size", "block_count", "trunc_voxel_multiplier"]
+    assert (p["voxel_size"].default, p["block_count"].default, p["trunc_voxel_multiplier"].default) == (0.0058, 40000, 8.0)
+    assert list(inspect.signature(MAP.integrate).parameters)[1:] == ["curr_rgbd", "i", "curr_global_pose"]
+    p = inspect.signature(TSDF.__init__).parameters
+    assert list(p)[1:3] == ["voxel_length", "sdf_trunc"] and (p["voxel_length"].default, p["sdf_trunc"].default) == (0.001, 0.1)
+    for cls in (MAP, TSDF):
+        for m in ("extract_pcd", "extract_mesh", "save_pcd", "save_mesh"):
+            assert callable(getattr(cls, m))
+    assert list(inspect.signature(TSDF.build_3D_map).parameters)[1:] == ["rgbd", "intrinsic", "extrinsic"]
+    assert list(inspect.signature(TSDF.build_copy_3D_map).parameters)[1:] == ["rgbd", "intrinsic", "extrinsic"]
+
+
+def test_stream_chunks_cover_the_trajectory_in_order():
+    from bodyslam_b200.tsdf import DenseTSDFVolume
+    for F in (1, 5, 255, 256, 257, 1000, 5000):
+        for ramp in ((), (64,), (32, 64, 128)):
+            for q in (1, 2, 8):
+                ch = DenseTSDFVolume.stream_chunks(F, 256, ramp=ramp, multiple_of=q)
+                assert ch[0][0] == 0 and ch[-1][1] == F and all(a[1] == b[0] for a, b in zip(ch, ch[1:]))
+                assert all(0 < f1 - f0 <= 256 + q for f0, f1 in ch)
+                assert all((f1 - f0) % q == 0 for f0, f1 in ch[:-1])

@@ -190,3 +190,63 @@ def test_cofactor_inverse_matches_lapack():
         out = np.zeros(16)
         oracle.o3d.lib().orc_invert4x4(E.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
         assert np.abs(out.reshape(4, 4) - np.linalg.inv(E)).max() < 1e-14
+
+
+def test_scalable_all_units_is_the_dense_rule_with_per_unit_arithmetic():
+    """`all_units=True` (the oracle of the product's unit_arithmetic mode): every unit is swept; it updates a superset of
+    what the activation rule updates, with identical values wherever both updated a voxel equally often; and it differs
+    from the brick-restart dense sweep only by float32 rounding of the voxel centres / the z recurrence"""
+    from util import small_scene
+    sc = small_scene("laparoscopy512", res=64, frames=3, with_color=False)
+    ul = sc["voxel_length"] * 32
+    origin = np.floor(sc["origin"] / ul + 0.5) * ul
+    A = oracle.o3d.Volume(64, sc["voxel_length"], sc["sdf_trunc"], origin)
+    S = oracle.o3d.Volume(64, sc["voxel_length"], sc["sdf_trunc"], origin)
+    D = oracle.o3d.Volume(64, sc["voxel_length"], sc["sdf_trunc"], origin)
+    for i in range(3):
+        d = oracle.o3d.depth_from_u16(sc["depth_u16"][i])
+        na = A.integrate_scalable(d, sc["K"], sc["E"][i], all_units=True)
+        ns = S.integrate_scalable(d, sc["K"], sc["E"][i])
+        nd = D.integrate(d, sc["K"], sc["E"][i], z_restart=8)
+        assert na >= ns > 0 and abs(na - nd) <= 0.01 * nd
+    assert np.all(A.weight >= S.weight)
+    same = A.weight == S.weight
+    assert np.array_equal(A.tsdf[same], S.tsdf[same])
+    agree = A.weight == D.weight
+    assert agree.mean() > 0.999 and np.abs(A.tsdf[agree] - D.tsdf[agree]).max() < 1e-3
+
+
+def test_vbg_oracle_on_a_fronto_parallel_plane():
+    """tensor-pipeline oracle (row f4): a plane at depth d seen from the identity pose -- voxels in front of it within
+    the truncation get the projective sdf (d - z) / trunc, voxels more than trunc behind it are untouched, only blocks
+    around the plane (and along the rays' [d - trunc, d + trunc] span) are activated"""
+    vs, res = 0.01, 64
+    origin = (-0.32, -0.32, 0.0)                   # blocks of 0.16 m: origin on the block grid
+    V = oracle.o3d.Volume(res, vs, 0.04, origin)
+    K = (300.0, 300.0, 159.5, 119.5)
+    depth = np.full((240, 320), 400, np.uint16)    # 0.4 m
+    n, touched = V.integrate_vbg(depth, K, np.eye(4), depth_scale=1000.0, depth_max=3.0, trunc_voxel_multiplier=4.0, return_touched=True)
+    assert n > 1000
+    zs = np.nonzero(touched.any(axis=(0, 1)))[0]
+    assert zs.min() == 2 and zs.max() <= 2 + 1     # 0.36 .. 0.44 m lies in block z = 2 (0.32 .. 0.48 m)
+    w, t = V.grid("weight"), V.grid("tsdf")
+    x = y = res // 2                                # near the optical axis; voxel z index k sits at z = k * vs (corner convention)
+    for k in range(32, 48):
+        z = np.float32(k) * np.float32(vs)
+        sdf = np.float32(0.4) - z
+        if sdf < -0.04 - 1e-6:
+            assert w[x, y, k] == 0
+        elif abs(sdf) < 0.04 - 1e-6:
+            assert w[x, y, k] == 1 and abs(t[x, y, k] - sdf / 0.04) < 1e-5
+    assert w[x, y, 10] == 0                         # free space far in front: its block was never activated
+    # depth_max cuts the frame off entirely
+    V2 = oracle.o3d.Volume(res, vs, 0.04, origin)
+    assert V2.integrate_vbg(depth, K, np.eye(4), depth_scale=1000.0, depth_max=0.3) == 0
+    # the extraction flavour of the tensor pipeline (weight >= 3) drops once-seen surface, the legacy rule keeps it
+    legacy = V.extract_mesh()
+    oracle.o3d.set_extract_flavour(3.0, 0.0)
+    try:
+        thr = V.extract_mesh()
+    finally:
+        oracle.o3d.set_extract_flavour(0.0, 0.5)
+    assert len(legacy["triangles"]) > 0 and len(thr["triangles"]) == 0
