@@ -142,9 +142,13 @@ __device__ double numpy_lerp(double a, double b, double t) {
 // per image are the long pole, so they are spread over kTableSlices SMs.
 constexpr int kTableSlices = 8;
 
+// phase 0: statistics + table in one launch (every slice CTA recomputes the statistics);  phase 1: statistics only
+// (grid (images, 1)) -> ImgStats;  phase 2: table only (grid (images, kTableSlices)) from the stored vmin / vmax.
+// The colorize / min-max paths launch phase 1 then phase 2: with phase 0 all 8 slice CTAs of an image re-read its
+// 256 KB histogram (134 MB of L2 traffic per 64 images, most of the pass's 49 us).
 __global__ void __launch_bounds__(1024) stats_table_kernel(void *ws, double p_lo, double p_hi, const double *vmin_vmax_override /*device*/,
                                                            double *vmin_vmax_out, double *median_out, int mode,
-                                                           const uint8_t *table_override) {
+                                                           const uint8_t *table_override, int phase) {
     __shared__ unsigned long long s_warp[32];
     __shared__ unsigned long long s_before[4];
     __shared__ int s_owner[4];
@@ -157,9 +161,18 @@ __global__ void __launch_bounds__(1024) stats_table_kernel(void *ws, double p_lo
     uint8_t *table = ws_table(ws, b);
     ImgStats *st = ws_stats(ws, b);
     if (table_override) { // value_transform path: the host supplies the table
-        for (int i = i_begin + t; i < i_end; i += 1024) table[i] = table_override[(size_t)b * kBins + i];
+        if (phase != 1)
+            for (int i = i_begin + t; i < i_end; i += 1024) table[i] = table_override[(size_t)b * kBins + i];
         return;
     }
+    if (phase == 2) {     // table only: the statistics were stored by the phase-1 launch
+        if (t == 0) {
+            s_vals[0] = st->vmin; s_vals[1] = st->vmax;
+            if (mode == 1) { s_vals[0] = (double)st->vmin_u; s_vals[1] = (double)st->vmax_u; }
+        }
+        __syncthreads();
+    }
+    if (phase != 2) {
     constexpr int kPer = kBins / 1024; // 64 consecutive bins per thread, fetched as 16-byte words
     unsigned long long local = 0;
     unsigned int lmin = 0xffffffffu, lmax = 0;
@@ -263,7 +276,8 @@ __global__ void __launch_bounds__(1024) stats_table_kernel(void *ws, double p_lo
         s_vals[0] = vmin; s_vals[1] = vmax;
     }
     __syncthreads();
-    if (mode == 2) return;
+    }   // phase != 2
+    if (mode == 2 || phase == 1) return;
     const double vmin = s_vals[0], vmax = s_vals[1];
     for (int i = i_begin + t; i < i_end; i += 1024) {
         unsigned int idx;
@@ -639,7 +653,9 @@ int bslam_colorize(const float *d_depth_m, const uint16_t *d_u16_in, int B, int 
         d_override = (double *)((char *)d_workspace + (size_t)B * kWsPerImage);
         BSLAM_CUDA(cudaMemcpyAsync(d_override, h_vmin_vmax, (size_t)B * 16, cudaMemcpyHostToDevice, st));
     }
-    stats_table_kernel<<<dim3((unsigned)B, kTableSlices), 1024, 0, st>>>(d_workspace, p_lo, p_hi, d_override, d_vmin_vmax_out, nullptr, 0, d_table_override);
+    stats_table_kernel<<<dim3((unsigned)B, 1), 1024, 0, st>>>(d_workspace, p_lo, p_hi, d_override, d_vmin_vmax_out, nullptr, 0, d_table_override, 1);
+    BSLAM_LAUNCH_CHECK();
+    stats_table_kernel<<<dim3((unsigned)B, kTableSlices), 1024, 0, st>>>(d_workspace, p_lo, p_hi, d_override, nullptr, nullptr, 0, d_table_override, 2);
     BSLAM_LAUNCH_CHECK();
     const uint16_t *src = d_depth_m ? d_u16_out : d_u16_in;
     const dim3 grid((unsigned)grid_for(n, 1024 * 4), (unsigned)B);
@@ -657,7 +673,9 @@ int bslam_minmax_u8(const uint16_t *d_u16, int B, int H, int W, uint8_t *d_gray,
     const int64_t n = (int64_t)H * W;
     int rc = run_hist(nullptr, d_u16, B, n, 1.0f, nullptr, 0, 0, d_workspace, st);
     if (rc) return rc;
-    stats_table_kernel<<<dim3((unsigned)B, kTableSlices), 1024, 0, st>>>(d_workspace, 0, 100, nullptr, nullptr, nullptr, 1, nullptr);
+    stats_table_kernel<<<dim3((unsigned)B, 1), 1024, 0, st>>>(d_workspace, 0, 100, nullptr, nullptr, nullptr, 1, nullptr, 1);
+    BSLAM_LAUNCH_CHECK();
+    stats_table_kernel<<<dim3((unsigned)B, kTableSlices), 1024, 0, st>>>(d_workspace, 0, 100, nullptr, nullptr, nullptr, 1, nullptr, 2);
     BSLAM_LAUNCH_CHECK();
     const dim3 grid((unsigned)grid_for(n, 1024 * 4), (unsigned)B);
     apply_table_kernel<3><<<grid, 256, 0, st>>>(d_u16, n, d_lut3, 0, 0, 0, d_rgb, d_gray, d_workspace);
@@ -671,7 +689,7 @@ int bslam_median_u16(const uint16_t *d_u16, int B, int64_t n_per_image, int has_
     cudaStream_t st = (cudaStream_t)stream;
     int rc = run_hist(nullptr, d_u16, B, n_per_image, 1.0f, nullptr, has_invalid, invalid_val, d_workspace, st);
     if (rc) return rc;
-    stats_table_kernel<<<dim3((unsigned)B, 1), 1024, 0, st>>>(d_workspace, 50, 50, nullptr, nullptr, d_out, 2, nullptr);
+    stats_table_kernel<<<dim3((unsigned)B, 1), 1024, 0, st>>>(d_workspace, 50, 50, nullptr, nullptr, d_out, 2, nullptr, 0);
     BSLAM_LAUNCH_CHECK();
     return BSLAM_OK;
 }
