@@ -65,6 +65,8 @@ _SIGNATURES = {
     "bslam_vbg_integrate": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.c_int, _p, _p, _p, C.c_float, C.c_float, _p, _p, _p]),
     "bslam_vbg_stats": (C.c_int, [_p, _p, _p]),
     "bslam_tsdf_set_extract_flavour": (C.c_int, [_p, C.c_float, C.c_double]),
+    "bslam_points_set_incremental": (C.c_int, [_p, C.c_int, C.c_int]),
+    "bslam_points_last_stats": (C.c_int, [_p, _p]),
     "bslam_points_count": (C.c_int, [_p, _p, _p]),
     "bslam_points_emit": (C.c_int, [_p, _p, _p, _p, _p, C.c_int64, _p]),
 }

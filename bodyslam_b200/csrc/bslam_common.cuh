@@ -129,6 +129,11 @@ struct bslam_volume {
     int batch; // frames per integrate launch (0 = default)
     int prof_enabled, prof_n;
     int zpw;                                  // z layers per integrate warp (0 = auto by shard size)
+    // incremental point extraction (bslam_points_set_incremental): per-brick cache of the extracted points
+    void *pts_cache;
+    size_t pts_cache_bytes;
+    int pts_incremental, pts_with_normals, pts_cache_valid, pts_counted;
+    long long pts_last_total, pts_last_candidates, pts_last_recomputed;
     // two-stream pipeline (bslam_tsdf_prepare_u16 / bslam_tsdf_integrate_prepared): second scratch buffer, two slots
     void *int_scratch2;
     void *slot_bp[2];                         // host copies of the prepared launches' parameters (BatchP)

@@ -398,6 +398,56 @@ __global__ void mc_list_kernel(int64_t nb, McScratch sc) {
         if (sc.cand[b]) sc.list[sc.cbase[b]] = (uint32_t)b;
 }
 
+// ---------------------------------------------------------------- incremental point extraction (row f1)
+// The SLAM loop extracts the point cloud after EVERY frame (N/3DM/slam.py:126,195) while a frame only changes the bricks
+// it sees.  K3 raises flag bit 2 ("changed since the last incremental extraction") on every brick it updates; a brick's
+// points depend on its own voxels and on its 26 neighbours' (the +1 voxel of an edge, the -1 .. +2 stencil of the
+// normals), so a brick is RE-EXTRACTED when any brick of its 3 x 3 x 3 neighbourhood carries the bit; every other
+// candidate brick's points are copied from a per-brick cache slot (<= 128 points; larger bricks are always recomputed).
+// The output is the same array, in the same order, as the full extraction's.
+constexpr uint32_t kNone = 0xffffffffu;
+constexpr int kSlotPts = 128;
+constexpr int kSlotWords = 13 * kSlotPts;      // xyz | normal | rgb | key(4) per point, structure of arrays inside a slot
+struct PtsCache {
+    uint32_t *slot;    // [nb] cache slot of the brick, kNone = none
+    uint32_t *cnt;     // [nb] cached point count, kNone = unknown / not cached -> recomputed every time
+    uint32_t *need;    // [nb] 1 = recompute in this extraction
+    uint32_t *used;    // [1] slots handed out so far
+    float *pool;       // [n_slots][kSlotWords]
+    uint32_t n_slots;
+};
+
+__global__ void pts_need_kernel(const VolView v, McScratch sc, PtsCache pc, int valid) {
+    const int64_t nb = brick_count(v);
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (int64_t)gridDim.x * blockDim.x) {
+        const bool cand = sc.cand[b] != 0;
+        bool need = false;
+        if (cand) {
+            need = !valid || pc.cnt[b] == kNone;
+            if (!need) {
+                const int bx = (int)(b % v.nbx), by = (int)((b / v.nbx) % v.nby), bz = (int)(b / ((int64_t)v.nbx * v.nby));
+                unsigned int any = 0;
+                for (int dz = -1; dz <= 1; ++dz)
+                    for (int dy = -1; dy <= 1; ++dy)
+                        for (int dx = -1; dx <= 1; ++dx) {
+                            const int x = bx + dx, y = by + dy, z = bz + dz;
+                            if (x >= 0 && y >= 0 && z >= 0 && x < v.nbx && y < v.nby && z < v.nbz) any |= v.flags[((int64_t)z * v.nby + y) * v.nbx + x] & 4u;
+                        }
+                need = any != 0;
+            }
+        }
+        pc.need[b] = need ? 1u : 0u;
+        sc.nvert[b] = (cand && !need) ? pc.cnt[b] : 0u;     // clean bricks keep their cached count; the count pass fills the others
+        if (need) atomicAdd(sc.totals + 3, 1ull);           // statistics: bricks recomputed by this extraction
+    }
+}
+
+__global__ void pts_clear_dirty_kernel(const VolView v) {
+    const int64_t nb = brick_count(v);
+    for (int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; b < nb; b += (int64_t)gridDim.x * blockDim.x)
+        if (v.flags[b] & 4u) v.flags[b] &= (uint8_t)~4u;
+}
+
 // ---------------------------------------------------------------- surface points (A.5)
 __device__ __forceinline__ bool pt_ok(const VolView &v, float2 t) { return t.y > v.w_min && t.x < 0.98f && t.x >= -0.98f; }
 
@@ -439,16 +489,42 @@ __device__ __forceinline__ double tsdf_at_staged(const float *s_t, double vl, do
     return t;
 }
 
+// pc.need != NULL: incremental mode (see above) -- the count pass only visits the bricks to recompute, the emit pass
+// recomputes those (and refreshes their cache slot) and copies the others from the cache
 template <bool EMIT>
 __global__ void __launch_bounds__(kBrickVox) points_brick_kernel(const VolView v, double vl, McScratch sc, float *points, float *normals,
-                                                                  float *colors, int32_t *keys, int64_t cap) {
+                                                                  float *colors, int32_t *keys, int64_t cap, PtsCache pc) {
     __shared__ uint32_t s_w[16];
     __shared__ float s_t[EMIT ? kPR * kPR * kPR : 1];
+    __shared__ uint32_t s_slot;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const unsigned int n_cand = (unsigned int)sc.totals[2];
   for (unsigned int ci = blockIdx.x; ci < n_cand; ci += gridDim.x) {      // persistent grid over the candidate list
     __syncthreads();
     const int64_t b = sc.list[ci];
+    const bool incremental = pc.need != nullptr;
+    if (incremental && !pc.need[b]) {
+        if (!EMIT) continue;
+        // clean brick: its points come from the cache, in the order they were emitted
+        const uint32_t n = sc.nvert[b], sl = pc.slot[b];
+        if (n == 0 || sl == kNone) continue;
+        const float *src = pc.pool + (size_t)sl * kSlotWords;
+        const int64_t o0 = (int64_t)sc.vbase[b];
+        for (uint32_t i = tid; i < n; i += kBrickVox) {
+            const int64_t o = o0 + i;
+            if (o >= cap) continue;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                points[3 * o + k] = src[k * kSlotPts + i];
+                if (normals) normals[3 * o + k] = src[(3 + k) * kSlotPts + i];
+                if (colors && v.color) colors[3 * o + k] = src[(6 + k) * kSlotPts + i];
+            }
+            if (keys)
+#pragma unroll
+                for (int k = 0; k < 4; ++k) keys[4 * o + k] = __float_as_int(src[(9 + k) * kSlotPts + i]);
+        }
+        continue;
+    }
     if (EMIT && sc.nvert[b] == 0) continue;
     const int bx = (int)(b % v.nbx), by = (int)((b / v.nbx) % v.nby), bz = (int)(b / ((int64_t)v.nbx * v.nby));
     if (EMIT && normals) {
@@ -487,11 +563,29 @@ __global__ void __launch_bounds__(kBrickVox) points_brick_kernel(const VolView v
     if (tid == 0) {
         uint32_t acc = 0;
         for (int w = 0; w < 16; ++w) { const uint32_t t = s_w[w]; s_w[w] = acc; acc += t; }
-        if (!EMIT) sc.nvert[b] = acc;
+        if (!EMIT) {
+            sc.nvert[b] = acc;
+            if (incremental && acc == 0) pc.cnt[b] = 0;      // nothing to cache: clean until a neighbour changes
+        } else if (incremental) {
+            // cache slot for the recomputed brick (kept if it has one; a new one while the pool lasts; none if too large)
+            uint32_t sl = kNone;
+            if (acc <= (uint32_t)kSlotPts) {
+                sl = pc.slot[b];
+                if (sl == kNone) {
+                    const uint32_t got = atomicAdd(pc.used, 1u);
+                    if (got < pc.n_slots) { sl = got; pc.slot[b] = sl; }
+                }
+            }
+            s_slot = sl;
+            pc.cnt[b] = (sl != kNone) ? acc : kNone;
+        }
     }
     __syncthreads();
     if (!EMIT || !cnt) continue;
-    int64_t o = (int64_t)sc.vbase[b] + s_w[wid] + (inc - cnt);
+    const int64_t li0 = (int64_t)s_w[wid] + (inc - cnt);        // index of this voxel's first point inside the brick
+    float *cache = (incremental && s_slot != kNone) ? pc.pool + (size_t)s_slot * kSlotWords : nullptr;
+    int64_t li = li0;
+    int64_t o = (int64_t)sc.vbase[b] + li0;
     const double half = vl * v.pos_half, half_gap = 0.99 * vl;
     const double p0[3] = {half + vl * X, half + vl * Y, half + vl * Z};
 #pragma unroll
@@ -505,6 +599,11 @@ __global__ void __launch_bounds__(kBrickVox) points_brick_kernel(const VolView v
             points[3 * o + 1] = (float)(p[1] + v.oy);
             points[3 * o + 2] = (float)(p[2] + v.oz + vl * v.gz0);
             if (keys) { keys[4 * o + 0] = X; keys[4 * o + 1] = Y; keys[4 * o + 2] = Z; keys[4 * o + 3] = a; }
+            if (cache) {
+                cache[0 * kSlotPts + li] = points[3 * o + 0]; cache[1 * kSlotPts + li] = points[3 * o + 1]; cache[2 * kSlotPts + li] = points[3 * o + 2];
+                cache[9 * kSlotPts + li] = __int_as_float(X); cache[10 * kSlotPts + li] = __int_as_float(Y);
+                cache[11 * kSlotPts + li] = __int_as_float(Z); cache[12 * kSlotPts + li] = __int_as_float(a);
+            }
             if (normals) {
                 double nn[3];
                 for (int k = 0; k < 3; ++k) {
@@ -513,7 +612,10 @@ __global__ void __launch_bounds__(kBrickVox) points_brick_kernel(const VolView v
                     nn[k] = tsdf_at_staged(s_t, vl, v.pos_half, bx * 8, by * 8, bz * 8, q1) - tsdf_at_staged(s_t, vl, v.pos_half, bx * 8, by * 8, bz * 8, q0);
                 }
                 const double len = sqrt(nn[0] * nn[0] + nn[1] * nn[1] + nn[2] * nn[2]);
-                for (int k = 0; k < 3; ++k) normals[3 * o + k] = (float)(len > 0 ? nn[k] / len : nn[k]);
+                for (int k = 0; k < 3; ++k) {
+                    normals[3 * o + k] = (float)(len > 0 ? nn[k] / len : nn[k]);
+                    if (cache) cache[(3 + k) * kSlotPts + li] = normals[3 * o + k];
+                }
             }
             if (colors && v.color) {
                 const int64_t s0 = b * kBrickVox + tid;
@@ -522,10 +624,11 @@ __global__ void __launch_bounds__(kBrickVox) points_brick_kernel(const VolView v
                     const double c0 = v.color[(s0 / kBrickVox) * (3 * kBrickVox) + k * kBrickVox + (s0 % kBrickVox)];
                     const double c1 = v.color[(s1 / kBrickVox) * (3 * kBrickVox) + k * kBrickVox + (s1 % kBrickVox)];
                     colors[3 * o + k] = (float)(((c0 * r1 + c1 * r0) / (r0 + r1)) / 255.0);
+                    if (cache) cache[(6 + k) * kSlotPts + li] = colors[3 * o + k];
                 }
             }
         }
-        ++o;
+        ++o; ++li;
     }
   }
 }
@@ -604,11 +707,48 @@ static int ensure_mc_scratch(bslam_volume *vol) {
     return BSLAM_OK;
 }
 
+static uint32_t pts_cache_slots(size_t nb) { return (uint32_t)(nb < 49152 ? nb : 49152); }
+static size_t pts_cache_bytes(size_t nb) {
+    return 3 * align_up(nb * 4, 256) + 256 + (size_t)pts_cache_slots(nb) * kSlotWords * sizeof(float);
+}
+static PtsCache carve_pts(void *p0, size_t nb) {
+    char *p = (char *)p0;
+    PtsCache c;
+    c.slot = (uint32_t *)p; p += align_up(nb * 4, 256);
+    c.cnt = (uint32_t *)p; p += align_up(nb * 4, 256);
+    c.need = (uint32_t *)p; p += align_up(nb * 4, 256);
+    c.used = (uint32_t *)p; p += 256;
+    c.pool = (float *)p;
+    c.n_slots = pts_cache_slots(nb);
+    return c;
+}
+static PtsCache no_cache() {
+    PtsCache c;
+    memset(&c, 0, sizeof(c));
+    return c;
+}
+
 } // namespace bslam
 
 using namespace bslam;
 
 extern "C" {
+
+int bslam_points_set_incremental(bslam_volume *vol, int enable, int with_normals) {
+    BSLAM_CHECK_ARG(vol != nullptr, "bslam_points_set_incremental: vol is NULL");
+    BSLAM_CHECK_ARG(!enable || (vol->v.gz0 == 0 && vol->v.zs == 1), "bslam_points_set_incremental: single-box volumes only");
+    vol->pts_incremental = enable ? 1 : 0;
+    vol->pts_with_normals = with_normals ? 1 : 0;
+    vol->pts_cache_valid = 0;
+    return BSLAM_OK;
+}
+
+int bslam_points_last_stats(const bslam_volume *vol, long long *h_stat2) {
+    BSLAM_CHECK_ARG(vol && h_stat2, "bslam_points_last_stats: NULL argument");
+    h_stat2[0] = vol->pts_last_candidates;
+    h_stat2[1] = vol->pts_last_recomputed;
+    return BSLAM_OK;
+}
 
 int bslam_mc_count(bslam_volume *vol, const float *d_halo_lo, const float *d_halo_hi, int64_t *h_counts, bslam_stream_t stream) {
     BSLAM_CHECK_ARG(vol && h_counts, "bslam_mc_count: NULL argument");
@@ -695,14 +835,41 @@ int bslam_points_count(bslam_volume *vol, int64_t *h_count, bslam_stream_t strea
     const McScratch sc = carve_mc(vol->mc_scratch, (size_t)nb);
     rc = build_candidates(vol, sc, 0, st);
     if (rc) return rc;
-    points_brick_kernel<false><<<kExtractGrid, kBrickVox, 0, st>>>(vol->v, vol->voxel_length_d, sc, nullptr, nullptr, nullptr, nullptr, 0);
+    PtsCache pc = no_cache();
+    if (vol->pts_incremental) {
+        const size_t need_bytes = pts_cache_bytes((size_t)nb);
+        if (!vol->pts_cache || vol->pts_cache_bytes < need_bytes) {
+            if (vol->pts_cache) cudaFree(vol->pts_cache);
+            vol->pts_cache = nullptr;
+            BSLAM_CUDA(cudaMalloc(&vol->pts_cache, need_bytes));
+            vol->pts_cache_bytes = need_bytes;
+            vol->pts_cache_valid = 0;
+        }
+        pc = carve_pts(vol->pts_cache, (size_t)nb);
+        if (!vol->pts_cache_valid) {    // slots, counts (0xffffffff = none / unknown) and the slot counter start over
+            BSLAM_CUDA(cudaMemsetAsync(vol->pts_cache, 0xff, 2 * align_up((size_t)nb * 4, 256), st));
+            BSLAM_CUDA(cudaMemsetAsync(pc.used, 0, 4, st));
+        }
+        const int g = num_sms(vol->device) * 4;
+        BSLAM_CUDA(cudaMemsetAsync(sc.totals + 3, 0, 8, st));
+        pts_need_kernel<<<g, 256, 0, st>>>(vol->v, sc, pc, vol->pts_cache_valid);
+        BSLAM_LAUNCH_CHECK();
+        pts_clear_dirty_kernel<<<g, 256, 0, st>>>(vol->v);
+        BSLAM_LAUNCH_CHECK();
+        vol->pts_cache_valid = 0;      // until the emit pass has refreshed the recomputed bricks' slots
+        vol->pts_counted = 1;
+    }
+    points_brick_kernel<false><<<kExtractGrid, kBrickVox, 0, st>>>(vol->v, vol->voxel_length_d, sc, nullptr, nullptr, nullptr, nullptr, 0, pc);
     BSLAM_LAUNCH_CHECK();
     rc = brick_scan(sc.nvert, nullptr, sc.vbase, nullptr, nb, sc.totals, sc.scan_ws, st);
     if (rc) return rc;
-    unsigned long long tot[2];
-    BSLAM_CUDA(cudaMemcpyAsync(tot, sc.totals, 16, cudaMemcpyDeviceToHost, st));
+    unsigned long long tot[4];
+    BSLAM_CUDA(cudaMemcpyAsync(tot, sc.totals, 32, cudaMemcpyDeviceToHost, st));
     BSLAM_CUDA(cudaStreamSynchronize(st));
     *h_count = (int64_t)tot[0];
+    vol->pts_last_total = (long long)tot[0];
+    vol->pts_last_candidates = (long long)tot[2];
+    vol->pts_last_recomputed = vol->pts_incremental ? (long long)tot[3] : (long long)tot[2];
     return BSLAM_OK;
 }
 
@@ -712,9 +879,19 @@ int bslam_points_emit(bslam_volume *vol, float *d_points, float *d_normals, floa
     BSLAM_DEVICE_GUARD(vol->device);
     const int64_t nb = brick_count(vol->v);
     const McScratch sc = carve_mc(vol->mc_scratch, (size_t)nb);
+    PtsCache pc = no_cache();
+    if (vol->pts_incremental) {
+        BSLAM_CHECK_ARG(vol->pts_cache && vol->pts_counted, "bslam_points_emit: incremental mode needs bslam_points_count before every emit");
+        BSLAM_CHECK_ARG(cap >= vol->pts_last_total, "bslam_points_emit: incremental mode needs room for all %lld points", vol->pts_last_total);
+        BSLAM_CHECK_ARG((d_normals != nullptr) == (vol->pts_with_normals != 0), "bslam_points_emit: incremental extraction was enabled %s normals",
+                        vol->pts_with_normals ? "with" : "without");
+        BSLAM_CHECK_ARG(!(vol->v.color && !d_colors), "bslam_points_emit: incremental extraction of a colour volume needs the colour output");
+        pc = carve_pts(vol->pts_cache, (size_t)nb);
+    }
     points_brick_kernel<true><<<kExtractGrid, kBrickVox, 0, (cudaStream_t)stream>>>(vol->v, vol->voxel_length_d, sc, d_points, d_normals, d_colors,
-                                                                                     d_keys, cap);
+                                                                                     d_keys, cap, pc);
     BSLAM_LAUNCH_CHECK();
+    if (vol->pts_incremental) { vol->pts_cache_valid = 1; vol->pts_counted = 0; }
     return BSLAM_OK;
 }
 

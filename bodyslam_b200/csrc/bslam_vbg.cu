@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(256) vbg_integrate_kernel(const VolView v, con
         if (dirty) {
             v.vox[slot] = tw;
             if (COLOR) { cp[0] = c[0]; cp[kBrickVox] = c[1]; cp[2 * kBrickVox] = c[2]; }
-            v.flags[slot / kBrickVox] = 3;     // touched + may hold a surface (extraction candidates)
+            v.flags[slot / kBrickVox] = 7;     // touched + may hold a surface (extraction candidates) + changed since the last incremental extraction
         }
     }
 }
@@ -256,6 +256,7 @@ int bslam_tsdf_set_extract_flavour(bslam_volume *vol, float weight_threshold, do
     // valid voxel <=> weight >= threshold (threshold 0: weight != 0, Open3D's legacy rule; weights are never negative)
     vol->v.w_min = weight_threshold > 0.f ? nextafterf(weight_threshold, 0.0f) : 0.0f;
     vol->v.pos_half = vertex_offset;
+    vol->pts_cache_valid = 0;
     return BSLAM_OK;
 }
 

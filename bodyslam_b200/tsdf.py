@@ -527,9 +527,31 @@ class DenseTSDFVolume:
         self.mc_emit(verts, keys, cols, tris, halo_lo, halo_hi)
         return TriangleMesh(verts, tris, cols, keys)
 
+    def set_incremental_points(self, enable: bool = True, normals: bool = True):
+        """incremental `extract_point_cloud` for the per-frame cadence (N/3DM/slam.py:126,195): only the bricks whose
+        neighbourhood an integration changed since the last extraction are re-extracted, the others come from a per-brick
+        cache; identical output.  `normals` fixes whether normals are produced in this mode."""
+        _lib.check(self._L.bslam_points_set_incremental(self._h, int(bool(enable)), int(bool(normals))))
+        self._pts_incremental = bool(enable)
+        self._pts_inc_normals = bool(normals)
+
+    def points_last_stats(self):
+        """(surface-candidate bricks, bricks recomputed) of the last extract_point_cloud"""
+        out = (C.c_longlong * 2)()
+        _lib.check(self._L.bslam_points_last_stats(self._h, out))
+        return int(out[0]), int(out[1])
+
     def extract_point_cloud(self, normals: bool = True) -> PointCloud:
         """Open3D `extract_point_cloud()` (tsdf.py:40)."""
         torch = _lib.require_cuda()
+        if getattr(self, "_pts_incremental", False) and bool(normals) != self._pts_inc_normals:
+            # a one-off request with the other normals setting: full extraction, the cache starts over afterwards
+            inc_n = self._pts_inc_normals
+            self.set_incremental_points(False)
+            try:
+                return self.extract_point_cloud(normals)
+            finally:
+                self.set_incremental_points(True, inc_n)
         cnt = np.zeros(1, np.int64)
         with torch.cuda.device(self.device):
             st = _lib.stream_ptr(self.device)
@@ -571,6 +593,7 @@ class TSDF:
         self.tsdf = self._make(origin, bool(unit_activation))
         if not unit_activation:
             self.tsdf.set_clip_check(8)
+        self.tsdf.set_incremental_points(True, normals=True)      # extract_pcd() runs after every frame in the reference's loop
         self._clip_warned = 0.0
         self._next_clip_check = 1      # frames_integrated at which the next (synchronising) clip check is due
 
@@ -605,6 +628,7 @@ class TSDF:
         self.tsdf = self._make(tuple(new_origin), bool(ua))
         if not ua:
             self.tsdf.set_clip_check(8)
+        self.tsdf.set_incremental_points(True, normals=True)
         warnings.warn(f"TSDF: only {100 * inside:.0f} % of the first frame's depth points fell inside the default box around the world "
                       f"origin; the box was re-centred on them: origin = ({new_origin[0]:.3f}, {new_origin[1]:.3f}, {new_origin[2]:.3f}) m, "
                       f"edge {ext[0]:.3f} m (pass origin= / resolution= to TSDF() to choose the box yourself)")

@@ -347,6 +347,15 @@ BSLAM_API int bslam_tsdf_set_extract_flavour(bslam_volume *vol, float weight_thr
  * voxels with w != 0 and -0.98 <= f < 0.98, sign change towards +x/+y/+z neighbour, linear
  * zero crossing; normals from the 0.99-voxel central difference of the trilinear TSDF.
  * Single-box volumes only (gz0 = 0 and no halos). */
+/* Incremental mode for the reference's per-frame cadence (extract_pcd after every build_3D_map, N/3DM/slam.py:126,195):
+ * the integration kernels flag the bricks they change; a count / emit pair then re-extracts only the bricks whose 3x3x3
+ * brick neighbourhood changed since the previous pair and copies every other brick's points from a per-brick cache
+ * (<= 128 points per brick; larger bricks are always recomputed).  Same output, same order as the full extraction.
+ * with_normals fixes whether normals are produced (bslam_points_emit must then be given / not given d_normals); colour
+ * volumes need d_colors; every bslam_points_emit needs its own bslam_points_count first and room for all points. */
+BSLAM_API int bslam_points_set_incremental(bslam_volume *vol, int enable, int with_normals);
+/* {surface-candidate bricks, bricks recomputed} of the last bslam_points_count (host values, no synchronisation) */
+BSLAM_API int bslam_points_last_stats(const bslam_volume *vol, long long *h_stat2);
 BSLAM_API int bslam_points_count(bslam_volume *vol, int64_t *h_count, bslam_stream_t stream);
 BSLAM_API int bslam_points_emit(bslam_volume *vol, float *d_points, float *d_normals,
                                 float *d_colors, int32_t *d_keys, int64_t cap,

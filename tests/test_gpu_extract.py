@@ -136,3 +136,49 @@ def test_surface_points_match_oracle(cuda, kind, n):
     assert np.array_equal(cg[og], co[oo])
     assert np.abs(pcd.points.cpu().numpy()[og] - ref["points"][oo]).max() <= 1e-4 * 0.01 + 1e-6
     assert np.abs(pcd.normals.cpu().numpy()[og] - ref["normals"][oo]).max() <= 1e-4
+
+
+@pytest.mark.parametrize("unit", [False, True])
+def test_incremental_point_extraction_equals_full_extraction(cuda, unit):
+    """row f1: `extract_pcd` after every frame (N/3DM/slam.py:126,195) in incremental mode -- only the bricks whose 3x3x3
+    neighbourhood the integration changed are re-extracted, the rest comes from the per-brick cache -- gives exactly the
+    arrays of a full extraction (points, normals, colours, keys, same order), frame after frame"""
+    import copy
+    from bodyslam_b200 import ops
+    from bodyslam_b200.tsdf import DenseTSDFVolume
+    sc = small_scene("laparoscopy512", res=96, frame_ids=np.arange(0, 120, 10))
+    origin = sc["origin"]
+    if unit:
+        ul = sc["voxel_length"] * 32
+        origin = np.floor(origin / ul + 0.5) * ul
+    vol = DenseTSDFVolume(sc["voxel_length"], sc["sdf_trunc"], 96, origin, color=True, device=cuda, unit_activation=unit)
+    vol.set_incremental_points(True, normals=True)
+    depth = ops.depth_from_u16(sc["depth_u16"], 1000.0, 3.0, cuda)
+    col = torch.from_numpy(sc["color"]).to(cuda)
+    recomputed = []
+    for i in range(len(sc["E"])):
+        vol.integrate_batch(depth[i:i + 1], col[i:i + 1], sc["intrinsic"], sc["E"][i:i + 1])
+        inc = vol.extract_point_cloud()
+        cand, rec = vol.points_last_stats()
+        recomputed.append(rec / max(cand, 1))
+        ref = copy.deepcopy(vol).extract_point_cloud()          # a fresh volume: full extraction
+        assert inc.points.shape[0] == ref.points.shape[0] > 1000
+        for a, b in ((inc.points, ref.points), (inc.normals, ref.normals), (inc.colors, ref.colors), (inc.point_keys, ref.point_keys)):
+            assert torch.equal(a, b)
+    assert recomputed[0] == 1.0
+    # nothing integrated since: (almost) nothing is recomputed -- only bricks too large for a cache slot
+    again = vol.extract_point_cloud()
+    cand, rec = vol.points_last_stats()
+    assert rec <= 0.05 * cand and torch.equal(again.points, inc.points) and torch.equal(again.normals, inc.normals)
+    # a one-off request without normals falls back to a full extraction and the cache starts over
+    nn = vol.extract_point_cloud(normals=False)
+    assert nn.normals is None and torch.equal(nn.points, inc.points)
+    full_again = vol.extract_point_cloud()
+    assert vol.points_last_stats()[1] == vol.points_last_stats()[0] and torch.equal(full_again.normals, inc.normals)
+    # reset invalidates the cache
+    vol.reset()
+    assert vol.extract_point_cloud().points.shape[0] == 0
+    vol.integrate_batch(depth[:1], col[:1], sc["intrinsic"], sc["E"][:1])
+    first = vol.extract_point_cloud()
+    ref = copy.deepcopy(vol).extract_point_cloud()
+    assert torch.equal(first.points, ref.points) and torch.equal(first.normals, ref.normals)
