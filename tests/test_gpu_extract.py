@@ -146,12 +146,10 @@ def test_incremental_point_extraction_equals_full_extraction(cuda, unit):
     import copy
     from bodyslam_b200 import ops
     from bodyslam_b200.tsdf import DenseTSDFVolume
-    sc = small_scene("laparoscopy512", res=96, frame_ids=np.arange(0, 120, 10))
+    res = 128 if unit else 96                     # 128: the scene's box already sits on the 32-voxel unit grid
+    sc = small_scene("laparoscopy512", res=res, frame_ids=np.arange(0, 120, 10))
     origin = sc["origin"]
-    if unit:
-        ul = sc["voxel_length"] * 32
-        origin = np.floor(origin / ul + 0.5) * ul
-    vol = DenseTSDFVolume(sc["voxel_length"], sc["sdf_trunc"], 96, origin, color=True, device=cuda, unit_activation=unit)
+    vol = DenseTSDFVolume(sc["voxel_length"], sc["sdf_trunc"], res, origin, color=True, device=cuda, unit_activation=unit)
     vol.set_incremental_points(True, normals=True)
     depth = ops.depth_from_u16(sc["depth_u16"], 1000.0, 3.0, cuda)
     col = torch.from_numpy(sc["color"]).to(cuda)
@@ -162,7 +160,7 @@ def test_incremental_point_extraction_equals_full_extraction(cuda, unit):
         cand, rec = vol.points_last_stats()
         recomputed.append(rec / max(cand, 1))
         ref = copy.deepcopy(vol).extract_point_cloud()          # a fresh volume: full extraction
-        assert inc.points.shape[0] == ref.points.shape[0] > 1000
+        assert inc.points.shape[0] == ref.points.shape[0] > 100, (i, inc.points.shape[0], ref.points.shape[0])
         for a, b in ((inc.points, ref.points), (inc.normals, ref.normals), (inc.colors, ref.colors), (inc.point_keys, ref.point_keys)):
             assert torch.equal(a, b)
     assert recomputed[0] == 1.0
