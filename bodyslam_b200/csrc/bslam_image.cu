@@ -41,24 +41,60 @@ constexpr int kHistThreads = 256;
 constexpr int kPxPerThread = 16;
 constexpr int kPxPerBlock = kHistThreads * kPxPerThread;
 constexpr int kWindow = 4096;
+constexpr int kHistMergeDefault = 2;
 
-template <bool FROM_FLOAT>
+// MERGE: how equal values are combined before they reach the shared-memory atomics (<= 2 lanes per cycle and SM, so
+// smooth images must not spend one atomic per pixel):
+//   0 = run-length merge over the thread's 16 pixels (17 compare / flush sites; issue-bound at ~50 instructions per pixel);
+//   1 = one atomic per 4-pixel group when its pixels are equal, else one per pixel (16-byte zero / flush of the window);
+//   2 = 1 + the equal groups of a warp are combined with match.any (one atomic per distinct value and warp).
+template <bool FROM_FLOAT, int MERGE>
 __global__ void __launch_bounds__(kHistThreads) scale_hist_kernel(const float *__restrict__ depth_m, const uint16_t *__restrict__ u16_in,
                                                                    uint16_t *__restrict__ u16_out, int64_t n_per_image, float scale_mul,
                                                                    int has_invalid, unsigned int invalid_val, void *ws) {
-    __shared__ unsigned int s_hist[kWindow];
+    __shared__ __align__(16) unsigned int s_hist[kWindow];
     __shared__ unsigned int s_min;
     const int b = blockIdx.y;
     const int64_t start = (int64_t)blockIdx.x * kPxPerBlock;
     unsigned int *hist = ws_hist(ws, b);
-    for (int i = threadIdx.x; i < kWindow; i += kHistThreads) s_hist[i] = 0;
+    if (MERGE == 0) {
+        for (int i = threadIdx.x; i < kWindow; i += kHistThreads) s_hist[i] = 0;
+    } else {
+        for (int i = threadIdx.x; i < kWindow / 4; i += kHistThreads) reinterpret_cast<uint4 *>(s_hist)[i] = make_uint4(0, 0, 0, 0);
+    }
     if (threadIdx.x == 0) s_min = 0xffffffffu;
     __syncthreads();
 
     unsigned int val[kPxPerThread];
     unsigned int tmin = 0xffffffffu;
     const int64_t img_off = (int64_t)b * n_per_image;
+    // a value no pixel can hold when there is no invalid marker: one compare + select per pixel either way
+    const unsigned int inv = has_invalid ? invalid_val : 0xfffffffeu;
     // thread t handles 4 groups of 4 consecutive pixels, groups strided by 1024 -> 16-byte accesses
+    if (MERGE != 0 && start + kPxPerBlock <= n_per_image && ((img_off + start) & 3) == 0) {
+        // the whole block lies inside the image and its rows of 4 are 16-byte aligned: no per-group tests
+        const int64_t q = img_off + start + threadIdx.x * 4;
+#pragma unroll
+        for (int g = 0; g < kPxPerThread / 4; ++g) {
+            if (FROM_FLOAT) {
+                const float4 d = *reinterpret_cast<const float4 *>(depth_m + q + g * (kHistThreads * 4));
+                val[4 * g + 0] = to_u16_sat(d.x, scale_mul); val[4 * g + 1] = to_u16_sat(d.y, scale_mul);
+                val[4 * g + 2] = to_u16_sat(d.z, scale_mul); val[4 * g + 3] = to_u16_sat(d.w, scale_mul);
+                if (u16_out)
+                    *reinterpret_cast<ushort4 *>(u16_out + q + g * (kHistThreads * 4)) =
+                        make_ushort4((unsigned short)val[4 * g], (unsigned short)val[4 * g + 1], (unsigned short)val[4 * g + 2], (unsigned short)val[4 * g + 3]);
+            } else {
+                const ushort4 d = *reinterpret_cast<const ushort4 *>(u16_in + q + g * (kHistThreads * 4));
+                val[4 * g + 0] = d.x; val[4 * g + 1] = d.y; val[4 * g + 2] = d.z; val[4 * g + 3] = d.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                unsigned int &x = val[4 * g + j];
+                x = (x == inv) ? 0xffffffffu : x;
+                tmin = min(tmin, x);
+            }
+        }
+    } else {
 #pragma unroll
     for (int g = 0; g < kPxPerThread / 4; ++g) {
         const int64_t p = start + (int64_t)g * (kHistThreads * 4) + threadIdx.x * 4;
@@ -94,35 +130,89 @@ __global__ void __launch_bounds__(kHistThreads) scale_hist_kernel(const float *_
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             unsigned int &x = val[4 * g + j];
-            if (x != 0xffffffffu && has_invalid && x == invalid_val) x = 0xffffffffu;
+            x = (x == inv) ? 0xffffffffu : x;
             tmin = min(tmin, x);
         }
+    }
     }
     for (int o = 16; o; o >>= 1) tmin = min(tmin, __shfl_xor_sync(0xffffffffu, tmin, o));
     if ((threadIdx.x & 31) == 0 && tmin != 0xffffffffu) atomicMin(&s_min, tmin);
     __syncthreads();
     const unsigned int base = s_min;
     if (base == 0xffffffffu) return; // no valid pixel in this block
-    // run-length merge inside the thread, then shared (window) or global atomics
-    unsigned int run_v = 0xffffffffu, run_n = 0;
+    if (MERGE == 0) {
+        // run-length merge inside the thread, then shared (window) or global atomics
+        unsigned int run_v = 0xffffffffu, run_n = 0;
 #pragma unroll
-    for (int i = 0; i <= kPxPerThread; ++i) {
-        const unsigned int x = (i < kPxPerThread) ? val[i] : 0xffffffffu;
-        if (x == run_v && x != 0xffffffffu) {
-            ++run_n;
-        } else {
-            if (run_n) {
-                const unsigned int rel = run_v - base;
-                if (rel < kWindow) atomicAdd(&s_hist[rel], run_n);
-                else atomicAdd(&hist[run_v], run_n);
+        for (int i = 0; i <= kPxPerThread; ++i) {
+            const unsigned int x = (i < kPxPerThread) ? val[i] : 0xffffffffu;
+            if (x == run_v && x != 0xffffffffu) {
+                ++run_n;
+            } else {
+                if (run_n) {
+                    const unsigned int rel = run_v - base;
+                    if (rel < kWindow) atomicAdd(&s_hist[rel], run_n);
+                    else atomicAdd(&hist[run_v], run_n);
+                }
+                run_v = x; run_n = (x != 0xffffffffu) ? 1u : 0u;
             }
-            run_v = x; run_n = (x != 0xffffffffu) ? 1u : 0u;
         }
+        __syncthreads();
+        for (int i = threadIdx.x; i < kWindow; i += kHistThreads) {
+            const unsigned int c = s_hist[i];
+            if (c) atomicAdd(&hist[base + i], c);
+        }
+        return;
+    }
+    // the marker 0xffffffff never lands in the window (base <= 65535), so only the global path tests for it
+    auto add = [&](unsigned int x, unsigned int n) {
+        const unsigned int rel = x - base;
+        if (rel < kWindow) atomicAdd(&s_hist[rel], n);
+        else if (x != 0xffffffffu) atomicAdd(&hist[x], n);
+    };
+    // the increment of the per-pixel path is kept opaque: with a literal 1 ptxas emits ATOMS.POPC.INC, which matches addresses
+    // across the warp first and runs at half the rate of ATOMS.ADD when the addresses are spread (white noise: 1.07 vs 0.50 ms)
+    // (n_per_image >= 1 here, so this is 1 -- but ptxas cannot know; an empty asm barrier is not enough, it leaves no PTX behind)
+    const unsigned int one = (unsigned int)min(n_per_image, (int64_t)1);
+#pragma unroll
+    for (int g = 0; g < kPxPerThread / 4; ++g) {
+        const unsigned int a = val[4 * g], c1 = val[4 * g + 1], c2 = val[4 * g + 2], c3 = val[4 * g + 3];
+        const bool uni = (a == c1) & (c1 == c2) & (c2 == c3);
+        if (MERGE == 2) {
+            // lanes whose group is equal AND holds the same value elect their lowest lane; a mixed group matches nobody
+            const unsigned int peers = __match_any_sync(0xffffffffu, uni ? a : (0xffff0000u | (threadIdx.x & 31)));
+            if (uni) {
+                if ((threadIdx.x & 31) == __ffs(peers) - 1) add(a, 4u * __popc(peers));
+                continue;
+            }
+        } else if (uni) {
+            add(a, 4u);
+            continue;
+        }
+        add(a, one); add(c1, one); add(c2, one); add(c3, one);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < kWindow; i += kHistThreads) {
-        const unsigned int c = s_hist[i];
-        if (c) atomicAdd(&hist[base + i], c);
+    // flush: 16-byte reads find the (on depth images: few) occupied bins.  Where a warp's 128-bin segment is densely
+    // occupied it is re-read word-interleaved, so that one global reduction covers 32 consecutive bins = 4 sectors; with
+    // the 16-byte ownership every reduction would touch 16 sectors, 2 bins each, and the L2 atomic units take a dense
+    // window (white noise) at a quarter of the rate: 1.07 instead of 0.50 ms per 64 x 1080p.
+    const int lane = threadIdx.x & 31;
+    for (int i = threadIdx.x; i < kWindow / 4; i += kHistThreads) {   // same trip count for every thread
+        const uint4 c = reinterpret_cast<const uint4 *>(s_hist)[i];
+        const bool nz = (c.x | c.y | c.z | c.w) != 0;
+        if (__popc(__ballot_sync(0xffffffffu, nz)) > 8) {
+            const int seg = 4 * (i - lane);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const unsigned int w = s_hist[seg + 32 * k + lane];
+                if (w) atomicAdd(&hist[base + seg + 32 * k + lane], w);
+            }
+        } else if (nz) {
+            if (c.x) atomicAdd(&hist[base + 4 * i + 0], c.x);
+            if (c.y) atomicAdd(&hist[base + 4 * i + 1], c.y);
+            if (c.z) atomicAdd(&hist[base + 4 * i + 2], c.z);
+            if (c.w) atomicAdd(&hist[base + 4 * i + 3], c.w);
+        }
     }
 }
 
@@ -629,8 +719,20 @@ static int run_hist(const float *d_depth_m, const uint16_t *d_u16_in, int B, int
                     int has_invalid, uint16_t invalid_val, void *ws, cudaStream_t st) {
     BSLAM_CUDA(cudaMemsetAsync(ws, 0, bslam_colorize_workspace_bytes(B), st));
     const dim3 grid((unsigned)((n + kPxPerBlock - 1) / kPxPerBlock), (unsigned)B);
-    if (d_depth_m) scale_hist_kernel<true><<<grid, kHistThreads, 0, st>>>(d_depth_m, nullptr, d_u16_out, n, scale_mul, has_invalid, invalid_val, ws);
-    else scale_hist_kernel<false><<<grid, kHistThreads, 0, st>>>(nullptr, d_u16_in, nullptr, n, scale_mul, has_invalid, invalid_val, ws);
+    static const int merge = [] {   // BSLAM_K1_MERGE = 0 | 1 | 2 selects the merge scheme (measurement switch; same histogram either way)
+        const char *e = getenv("BSLAM_K1_MERGE");
+        const int m = e ? atoi(e) : kHistMergeDefault;
+        return (m >= 0 && m <= 2) ? m : kHistMergeDefault;
+    }();
+#define BSLAM_HIST(M_)                                                                                                                       \
+    do {                                                                                                                                     \
+        if (d_depth_m) scale_hist_kernel<true, M_><<<grid, kHistThreads, 0, st>>>(d_depth_m, nullptr, d_u16_out, n, scale_mul, has_invalid, invalid_val, ws); \
+        else scale_hist_kernel<false, M_><<<grid, kHistThreads, 0, st>>>(nullptr, d_u16_in, nullptr, n, scale_mul, has_invalid, invalid_val, ws);             \
+    } while (0)
+    if (merge == 0) BSLAM_HIST(0);
+    else if (merge == 1) BSLAM_HIST(1);
+    else BSLAM_HIST(2);
+#undef BSLAM_HIST
     BSLAM_LAUNCH_CHECK();
     return BSLAM_OK;
 }
