@@ -21,6 +21,12 @@ def child():
     d1080, _ = S.render(cfg["surface"], Eb, K=K1080, W=Ww, H=Hh, device=dev, with_color=False)
     metres = (d1080.to(torch.float32) / 1000.0).contiguous()
     del d1080
+    if os.environ.get("K1AB_QUICK"):      # profiler runs: the rendered input only
+        lut = mdem.get_cmap_lut("viridis")
+        for _ in range(6):
+            ops.colorize_u16(lut, depth_m=metres, invalid_val=0)
+        torch.cuda.synchronize()
+        return
     g = torch.Generator(device=dev).manual_seed(1)
     noise = (torch.rand((B, Hh, Ww), device=dev, generator=g) * 10.0).contiguous()
     lut = mdem.get_cmap_lut("viridis")
