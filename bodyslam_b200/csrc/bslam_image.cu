@@ -746,6 +746,9 @@ int bslam_colorize(const float *d_depth_m, const uint16_t *d_u16_in, int B, int 
     BSLAM_CHECK_ARG(d_rgba && d_lut && d_workspace, "bslam_colorize: NULL output / lut / workspace");
     BSLAM_CHECK_ARG(!(d_depth_m && !d_u16_out), "bslam_colorize: float input needs d_u16_out (the metric-scaled image)");
     BSLAM_CHECK_ARG(p_lo >= 0 && p_lo <= 100 && p_hi >= 0 && p_hi <= 100, "bslam_colorize: percentiles must be in [0,100]");
+    // the kernels read 4 pixels per access: float4 / ushort4 / uchar4 x 4
+    BSLAM_CHECK_ARG(((uintptr_t)d_depth_m & 15) == 0 && ((uintptr_t)d_u16_in & 7) == 0 && ((uintptr_t)d_u16_out & 7) == 0 && ((uintptr_t)d_rgba & 15) == 0,
+                    "bslam_colorize: depth / rgba buffers must be 16-byte aligned, u16 buffers 8-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n = (int64_t)H * W;
     int rc = run_hist(d_depth_m, d_u16_in, B, n, scale_mul, d_u16_out, has_invalid, invalid_val, d_workspace, st);
@@ -771,6 +774,7 @@ int bslam_minmax_u8(const uint16_t *d_u16, int B, int H, int W, uint8_t *d_gray,
     BSLAM_CHECK_ARG(d_u16 && d_workspace && B > 0 && H > 0 && W > 0 && B <= 65535, "bslam_minmax_u8: bad argument");
     BSLAM_CHECK_ARG(d_gray || d_rgb, "bslam_minmax_u8: no output requested");
     BSLAM_CHECK_ARG(!(d_rgb && !d_lut3), "bslam_minmax_u8: colour output needs a 256x3 LUT");
+    BSLAM_CHECK_ARG(((uintptr_t)d_u16 & 7) == 0, "bslam_minmax_u8: the u16 buffer must be 8-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n = (int64_t)H * W;
     int rc = run_hist(nullptr, d_u16, B, n, 1.0f, nullptr, 0, 0, d_workspace, st);
@@ -788,6 +792,7 @@ int bslam_minmax_u8(const uint16_t *d_u16, int B, int H, int W, uint8_t *d_gray,
 int bslam_median_u16(const uint16_t *d_u16, int B, int64_t n_per_image, int has_invalid, uint16_t invalid_val, double *d_out,
                      void *d_workspace, bslam_stream_t stream) {
     BSLAM_CHECK_ARG(d_u16 && d_out && d_workspace && B > 0 && B <= 65535 && n_per_image > 0, "bslam_median_u16: bad argument");
+    BSLAM_CHECK_ARG(((uintptr_t)d_u16 & 7) == 0, "bslam_median_u16: the u16 buffer must be 8-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     int rc = run_hist(nullptr, d_u16, B, n_per_image, 1.0f, nullptr, has_invalid, invalid_val, d_workspace, st);
     if (rc) return rc;

@@ -35,6 +35,12 @@ def as_cuda(x, dtype, device=None):
     return x.to(dev, non_blocking=True).contiguous()
 
 
+def _aligned(x, nbytes=16):
+    """the image kernels read 4 pixels per access: a contiguous view whose base is not `nbytes`-aligned (a slice of a
+    larger buffer) is re-packed into its own allocation; torch allocations themselves are 512-byte aligned."""
+    return x.clone() if x.data_ptr() % nbytes else x
+
+
 def _dtype_name(x):
     return str(x.dtype if hasattr(x, "dtype") else to_numpy(x).dtype).replace("torch.", "")
 
@@ -64,7 +70,7 @@ def scale_to_u16(depth_m, scale=256.0, device=None):
     """a1: `(metres * 256).astype(uint16)` -- ZoeDepth's infer_pil(output_type='pil') tail."""
     torch = _lib.require_cuda()
     dev = _device(device)
-    src = as_cuda(depth_m, torch.float32, dev)
+    src = _aligned(as_cuda(depth_m, torch.float32, dev))
     out = torch.empty(src.shape, dtype=torch.uint16, device=dev)
     with torch.cuda.device(dev):
         _lib.check(_lib.load().bslam_scale_u16(_lib.ptr(src), src.numel(), float(scale), _lib.ptr(out), _lib.stream_ptr(dev)))
@@ -90,7 +96,7 @@ def colorize_u16(lut_rgba, depth_m=None, depth_u16=None, scale=256.0, invalid_va
     L = _lib.load()
     if (depth_m is None) == (depth_u16 is None):
         raise ValueError("give exactly one of depth_m / depth_u16")
-    src = as_cuda(depth_m, torch.float32, dev) if depth_m is not None else as_cuda(depth_u16, torch.uint16, dev)
+    src = _aligned(as_cuda(depth_m, torch.float32, dev) if depth_m is not None else as_cuda(depth_u16, torch.uint16, dev))
     squeeze = src.dim() == 2
     if squeeze:
         src = src.unsqueeze(0)
@@ -166,7 +172,7 @@ def minmax_colormap(depth_u16, lut_bgr=None, device=None):
     torch = _lib.require_cuda()
     dev = _device(device)
     L = _lib.load()
-    src = as_cuda(depth_u16, torch.uint16, dev)
+    src = _aligned(as_cuda(depth_u16, torch.uint16, dev))
     squeeze = src.dim() == 2
     if squeeze:
         src = src.unsqueeze(0)
@@ -190,7 +196,7 @@ def median_u16(x_u16, invalid_val=None, device=None):
     torch = _lib.require_cuda()
     dev = _device(device)
     L = _lib.load()
-    src = as_cuda(x_u16, torch.uint16, dev)
+    src = _aligned(as_cuda(x_u16, torch.uint16, dev))
     if src.dim() == 1:
         src = src.unsqueeze(0)
     B = src.shape[0]

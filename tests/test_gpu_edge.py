@@ -141,3 +141,37 @@ def test_default_box_recentres_on_the_first_frame(cuda):
     assert np.allclose(t2.tsdf.origin, -0.256)
     with pytest.warns(UserWarning, match="outside the volume box"):
         t2.extract_pcd()
+
+
+def test_image_ops_take_misaligned_views(cuda):
+    """a contiguous view into a larger buffer (base only 4- / 2-byte aligned) gives the result of an aligned copy: the
+    Python ops re-pack it, and the C entry points refuse the raw pointer instead of faulting in a vector load"""
+    import ctypes
+    from bodyslam_b200 import _lib
+    rng = np.random.default_rng(5)
+    m = rng.uniform(0.05, 3.0, size=(3, 48, 64)).astype(np.float32)
+    m[rng.uniform(size=m.shape) < 0.05] = 0
+    lut = mdem.get_cmap_lut("viridis")
+    d = torch.from_numpy(m).to(cuda)
+    buf = torch.zeros(d.numel() + 1, dtype=torch.float32, device=cuda)
+    buf[1:] = d.reshape(-1)
+    view = buf[1:].view(d.shape)
+    assert view.data_ptr() % 16 != 0 and view.is_contiguous()
+    rgba_a, u16_a = ops.colorize_u16(lut, depth_m=d, invalid_val=0)
+    rgba_v, u16_v = ops.colorize_u16(lut, depth_m=view, invalid_val=0)
+    assert torch.equal(rgba_a, rgba_v) and torch.equal(u16_a, u16_v)
+    assert torch.equal(ops.scale_to_u16(view), ops.scale_to_u16(d))
+    ubuf = torch.zeros(u16_a.numel() + 1, dtype=torch.uint16, device=cuda)
+    ubuf[1:] = u16_a.reshape(-1)
+    uview = ubuf[1:].view(u16_a.shape)
+    assert uview.data_ptr() % 8 != 0
+    assert torch.equal(ops.colorize_u16(lut, depth_u16=uview, invalid_val=0)[0], rgba_a)
+    assert torch.equal(ops.median_u16(uview, invalid_val=0), ops.median_u16(u16_a, invalid_val=0))
+    assert torch.equal(ops.minmax_colormap(uview)[0], ops.minmax_colormap(u16_a)[0])
+    # the C ABI itself: a misaligned pointer is an argument error, not a CUDA fault
+    L = _lib.load()
+    ws = torch.empty(L.bslam_colorize_workspace_bytes(3), dtype=torch.uint8, device=cuda)
+    out = torch.empty(3, dtype=torch.float64, device=cuda)
+    rc = L.bslam_median_u16(_lib.ptr(uview), 3, 48 * 64, 0, 0, _lib.ptr(out), _lib.ptr(ws), _lib.stream_ptr(cuda))
+    assert rc != 0 and "aligned" in L.bslam_last_error().decode()
+    torch.cuda.synchronize()
